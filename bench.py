@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- read-bases classified per second on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+Workload (config.workload = "c2"): BASELINE.json configs[1] -- 10 000 synthetic long
+reads (gamma lengths, mean 20 kb, ~0.2 Gbases) against 10 M + 10 M distinct random
+21-mers, per GPU (weak scaling: every rank classifies its own 10 000 reads against
+its own replica of both sets; no collective on the data path).
+
+A "step" is one pass of the hot path over that batch.
+  value  : bases/s with the batch already resident in HBM (pack + index + classify
+           + fix-up + decide kernels; CUDA events on the launching stream)
+  e2e    : bases/s through the C-ABI classifier with PINNED HOST buffers -- H2D copy of
+           the ASCII bases + offsets and D2H copy of counts/scores/bins inside the
+           timed region, two slots in flight (double-buffered streams)
+  roofline: classify kernel only: (32 B x probes + 0.25 B x bases) / kernel time
+           against the measured HBM copy peak, plus the measured random-32-B-sector
+           gather ceiling of the same GPU.
+Tables (2 x 160 MB) exceed the 126 MB L2, and every step re-reads them at random, so
+no explicit L2 flush is needed between iterations (config.l2 says so).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_reads, mean_len, k, n_a, n_b, fixed_len)
+    "c2": (10_000, 20_000, 21, 10_000_000, 10_000_000, False),
+    "c2_small": (1_000, 20_000, 21, 1_000_000, 1_000_000, False),   # quick local checks
+    "c5_slice": (1_000_000, 150, 21, 10_000_000, 10_000_000, True),  # short-read shape
+}
+METRIC = "read_bases_classified_per_sec"
+UNIT = "bases/s"
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+class Dist:
+    """torch.distributed as plumbing only: barrier + max/sum over ranks."""
+
+    def __init__(self, world, backend):
+        self.world = world
+        self.torch = None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+
+            self.torch, self.dist = torch, dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29531")
+            dist.init_process_group(backend=backend)
+            self.dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if backend == "nccl" else torch.device("cpu")
+            if backend == "nccl":
+                torch.cuda.set_device(self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def reduce(self, value, op):
+        if self.world == 1:
+            return value
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = os.path.join(tempfile.gettempdir(), f"tb_clocks_{os.getpid()}.csv")
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.f.close()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_workload(name, rank, tmp_dir):
+    from trio_binning_b200 import synth
+
+    n_reads, mean_len, k, n_a, n_b, fixed = WORKLOADS[name]
+    keys_a, keys_b, path_a, path_b = synth.materialise_sets(tmp_dir, n_a, n_b, k, seed=42)
+    bases, offsets, _ = synth.random_reads(n_reads, mean_len, k, keys_a, keys_b, seed=43 + rank,
+                                           plant_every=1000, fixed_len=fixed)
+    return dict(k=k, keys_a=keys_a, keys_b=keys_b, path_a=path_a, path_b=path_b,
+                bases=bases, offsets=offsets, n_reads=n_reads, mean_len=mean_len, n_a=n_a, n_b=n_b)
+
+
+# --------------------------------------------------------------------------- CPU arms
+def _ref_worker_init():
+    pass
+
+
+_REF = {}
+
+
+def _ref_count_range(args):
+    lo, hi = args
+    lib, A, B, bases, offsets = _REF["lib"], _REF["A"], _REF["B"], _REF["bases"], _REF["offsets"]
+    ca = cb = 0
+    n = 0
+    for r in range(lo, hi):
+        a, b = lib.count(bytes(bases[offsets[r]:offsets[r + 1]]), A, B)
+        ca += a
+        cb += b
+        n += int(offsets[r + 1] - offsets[r])
+    return n, ca, cb
+
+
+def cpu_reference_setup(wl):
+    """Load the reference's own CPU implementation (compiled from /root/reference/c/kmers.c
+    into oracle/_ref by oracle/build_oracle.py) and build both sets with it; fall back to
+    the oracle port if the compiled reference did not travel."""
+    from oracle.oracle import CompiledReference, Oracle
+
+    if CompiledReference.available():
+        lib = CompiledReference()
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(2)
+        os.dup2(devnull, 2)  # the reference prints progress to stderr
+        try:
+            A, B = lib.set_from_file(wl["path_a"]), lib.set_from_file(wl["path_b"])
+        finally:
+            os.dup2(saved, 2)
+            os.close(devnull)
+            os.close(saved)
+        kind = "reference"
+    else:
+        lib = Oracle()
+        A, B = lib.set_from_ints(wl["keys_a"], wl["k"]), lib.set_from_ints(wl["keys_b"], wl["k"])
+        kind = "port"
+    _REF.update(lib=lib, A=A, B=B, bases=wl["bases"], offsets=wl["offsets"])
+    return kind
+
+
+def cpu_time_reads(read_lo, read_hi, procs):
+    """Classify reads [read_lo, read_hi) on `procs` host processes (fork: the sets built
+    in the parent are shared copy-on-write).  Returns (bases, seconds)."""
+    import multiprocessing as mp
+
+    t0 = time.perf_counter()
+    if procs <= 1:
+        n, _, _ = _ref_count_range((read_lo, read_hi))
+    else:
+        bounds = np.linspace(read_lo, read_hi, procs * 4 + 1).astype(int)
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_ref_count_range, list(zip(bounds[:-1], bounds[1:])))
+        n = sum(r[0] for r in res)
+    return n, time.perf_counter() - t0
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return 0
+    tmp_dir = os.path.join(tempfile.gettempdir(), "tb_bench_data")
+    wl = build_workload(args.workload, 0, tmp_dir)
+    kind = cpu_reference_setup(wl)
+    procs = os.cpu_count() or 1
+    # bounded sample per step: ~2.5 s of work at ~0.8 Mbases/s/core
+    mean_len = wl["mean_len"]
+    reads_per_step = max(procs, int(2.5 * 0.8e6 * procs / mean_len))
+    reads_per_step = min(reads_per_step, wl["n_reads"])
+    times, bases_done = [], []
+    cursor = 0
+    for step in range(args.warmup + args.steps):
+        lo = cursor % max(1, wl["n_reads"] - reads_per_step + 1)
+        n, dt = cpu_time_reads(lo, lo + reads_per_step, procs)
+        cursor += reads_per_step
+        if step >= args.warmup:
+            times.append(dt)
+            bases_done.append(n)
+    total_t, total_b = sum(times), sum(bases_done)
+    value = total_b / total_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic", "config": workload_config(args, wl),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind,
+                         "sample": f"{reads_per_step} reads (~{total_b // args.steps} bases) per step, "
+                                   f"{procs} forked processes over reads, sets built once (untimed)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, wl):
+    return {"workload": f"{args.workload}: {wl['n_reads']} reads, mean {wl['mean_len']} bases, "
+                        f"k={wl['k']}, {wl['n_a']}+{wl['n_b']} distinct random {wl['k']}-mers "
+                        f"(raw orientation, ~50% findable), per GPU",
+            "reads_per_gpu": wl["n_reads"], "bases_per_gpu": int(wl["offsets"][-1]),
+            "k": wl["k"], "set_a": wl["n_a"], "set_b": wl["n_b"],
+            "l2": "tables (2 x 160 MB at load 0.5) exceed the 126 MB L2; random probes, no flush needed",
+            "parallelism": f"reads sharded over {args.gpus} GPU(s), sets replicated, no collective"}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args, rank, local_rank, world):
+    from trio_binning_b200 import kmers, synth
+
+    if kmers.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    dist = Dist(world, "nccl")
+    kmers.set_device(local_rank)
+    tmp_dir = os.path.join(tempfile.gettempdir(), f"tb_bench_data_r{rank}" if world > 1 else "tb_bench_data")
+    t_setup = time.perf_counter()
+    wl = build_workload(args.workload, rank, tmp_dir)
+    k = wl["k"]
+    A = kmers.create_kmer_hash_set(wl["path_a"])
+    B = kmers.create_kmer_hash_set(wl["path_b"])
+    build_ms = A.contents.build_ms + B.contents.build_ms
+    bases, offsets = wl["bases"], wl["offsets"]
+    total = int(offsets[-1])
+    n_reads = wl["n_reads"]
+    windows = synth.total_windows(offsets, k)
+
+    clf = kmers.Classifier(A, B, max_bases=total, max_reads=n_reads, n_slots=2)
+    for slot in range(2):  # fill the pinned staging buffers once: these ARE the host inputs
+        hb, ho = clf.staging(slot)
+        hb[:total] = bases
+        ho[: n_reads + 1] = offsets
+    setup_s = time.perf_counter() - t_setup
+
+    # ---- end to end: pinned host -> H2D -> kernels -> D2H, two slots in flight
+    def e2e_pass(n_steps):
+        clf.mark(0, 0)
+        for i in range(n_steps):
+            slot = i & 1
+            if i >= 2:
+                clf.wait(slot)  # results of the batch that used this slot two steps ago
+            clf.submit(slot, None, None, n_reads=n_reads)
+        clf.mark(0, 1)
+        clf.mark(1, 1)
+        clf.wait(0)
+        clf.wait(1)
+        return max(clf.elapsed_ms(0, 0, 0, 1), clf.elapsed_ms(0, 0, 1, 1))
+
+    e2e_pass(max(3, args.warmup))
+    ca, cb, sa, sb, bins = (x.copy() for x in clf.result(0))
+    hits_a = int(ca.sum())
+    probes = 2 * windows - hits_a
+
+    sampler = ClockSampler(local_rank)
+    dist.barrier()
+    sampler.start()
+    e2e_ms = e2e_pass(args.steps)
+    dist.barrier()
+    e2e_ms = dist.reduce(e2e_ms, "MAX")
+
+    # ---- HBM-resident: device part only, CUDA events on the slot's stream
+    clf.rerun_resident(0, max(3, args.warmup))
+    dist.barrier()
+    res_ms, cls_ms = clf.rerun_resident(0, args.steps)
+    dist.barrier()
+    clocks = sampler.stop()
+    res_ms_max = dist.reduce(res_ms, "MAX")
+    total_all = dist.reduce(total, "SUM")
+    probes_all = dist.reduce(probes, "SUM")
+
+    # results unchanged by the re-runs (idempotence of the device pipeline)
+    clf.submit(0, None, None, n_reads=n_reads)
+    ca2, cb2, *_ = clf.result(0)
+    assert (ca2 == ca).all() and (cb2 == cb).all(), "re-run changed the results"
+
+    line = None
+    if rank == 0:
+        hbm_gbs, peak_src = measured_peaks()
+        cls_ms_per = cls_ms / args.steps
+        algo_bytes = 32.0 * probes + 0.25 * total
+        achieved = algo_bytes / (cls_ms_per * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_classify<21,8>", "achieved": achieved, "peak": hbm_gbs,
+                    "unit": "GB/s", "frac": achieved / hbm_gbs, "peak_source": peak_src,
+                    "traffic": None,
+                    "algorithmic_bytes_per_launch": algo_bytes,
+                    "probes_per_launch": probes, "kernel_ms": cls_ms_per,
+                    "probes_per_s": probes / (cls_ms_per * 1e-3),
+                    "kernel_share_of_step": cls_ms / res_ms}
+        if not args.no_gather:
+            # random-32-B-sector gather ceiling of this GPU (north_star's probe roofline)
+            best = 0.0
+            for mlp, tpb, bps in ((8, 256, 8), (16, 256, 4), (4, 512, 4), (8, 128, 16)):
+                rate, _ = kmers.gather_bench(4 << 30, mlp, tpb, bps, 48, 0)
+                best = max(best, rate)
+            roofline["random_sector_ceiling_sectors_per_s"] = best
+            roofline["random_sector_ceiling_gbs"] = best * 32 / 1e9
+            roofline["frac_of_random_sector_ceiling"] = (probes / (cls_ms_per * 1e-3)) / best
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            kind = cpu_reference_setup(wl)
+            sample_reads = max(1, int(15e6 / wl["mean_len"]))  # ~15 Mbases: 15-20 s on one core
+            sample_reads = min(sample_reads, n_reads)
+            nb, dt = cpu_time_reads(0, sample_reads, 1)
+            cpu = {"value": nb / dt, "unit": UNIT, "cores": 1, "kind": kind,
+                   "sample": f"first {sample_reads} reads ({nb} bases) of the same batch, same full-size "
+                             f"sets, 1 process / 1 thread (the reference as shipped), {dt:.1f} s"}
+            # parity spot check while we are here: the sample's counts equal the GPU's
+            lib = _REF["lib"]
+            for r in range(0, sample_reads, max(1, sample_reads // 25)):
+                got = lib.count(bytes(bases[offsets[r]:offsets[r + 1]]), _REF["A"], _REF["B"])
+                assert got == (ca[r], cb[r]), f"parity failure on read {r}: cpu {got} gpu {(ca[r], cb[r])}"
+        line = {
+            "metric": METRIC, "value": total_all / (res_ms_max / args.steps * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": res_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": workload_config(args, wl),
+            "e2e": {"value": total_all / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": total + 8 * (n_reads + 1),
+                    "d2h_bytes_per_step": n_reads * (4 + 4 + 8 + 8 + 1),
+                    "ms_per_step": e2e_ms / args.steps,
+                    "api": "tb_classifier_submit/wait (C ABI), pinned host buffers, 2 slots in flight"},
+            "gpu_launches": 5 * args.steps,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "probes_per_s": probes_all / (res_ms_max / args.steps * 1e-3),
+            "set_build_ms": build_ms,
+            "setup_s": setup_s,
+            "bins": {"A": int((bins == 65).sum()), "B": int((bins == 66).sum()), "U": int((bins == 85).sum())},
+        }
+        print(json.dumps(line), flush=True)
+    clf.close()
+    dist.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+    return run_gpu_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,172 @@
+/*
+ * trio_kmers_b200.h -- C ABI of the B200-native replacement for trio_binning's
+ * native k-mer library (reference: c/kmers.c, loaded by src/trio_binning/kmers.py:30-38
+ * through ctypes).
+ *
+ * The shared library built from trio_binning_b200/csrc/ is called
+ * `kmers_c<EXT_SUFFIX>` so that the reference's own loader finds it.  It exports
+ *
+ *   (1) the LEGACY symbols the reference's kmers.py binds, with identical names,
+ *       argument meaning and struct prefix -- each backed by CUDA kernels on
+ *       sm_100a, no CPU fallback (a missing / failing device is an error), and
+ *   (2) a batched / streaming API (prefix tb_) that the reference does not have
+ *       and that a GPU needs: many reads per call, pinned host buffers,
+ *       double-buffered asynchronous slots, device selection, explicit destroy.
+ *
+ * Plain C types only: pointers, sizes, ints, doubles.  No torch types.
+ *
+ * Error convention for tb_* functions: return 0 on success, a negative code on
+ * failure; tb_last_error() returns a thread-local message.  Legacy functions
+ * keep the reference's signatures (no return codes): on failure
+ * create_kmer_hash_set returns NULL and count_kmers_in_read writes -1/-1 and
+ * records the message; they print it to stderr as well.
+ */
+#ifndef TRIO_KMERS_B200_H
+#define TRIO_KMERS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------
+ * Set handle.  The first 32 bytes are the reference's `hash_set`
+ * (c/kmers.c:12-38; mirrored by kmers.py:53-59): Python only ever reads
+ * `.contents.num_kmers` (kmers.py:157-159).  `kmers` / `full` are NULL -- the
+ * table lives in HBM -- and nothing on the host dereferences them.
+ * ---------------------------------------------------------------------- */
+typedef struct hash_set {
+    uint64_t *kmers;        /* always NULL on the host side                        */
+    unsigned char *full;    /* always NULL                                          */
+    int hash_size;          /* reference value num_kmers*4/3 (c/kmers.c:166)        */
+    unsigned char k;        /* k-mer length, 1..32                                  */
+    int num_kmers;          /* number of LINES of the k-mer file (c/kmers.c:131-136)*/
+    /* ---- B200 extension (opaque to callers) ---- */
+    uint32_t magic;         /* 'TB20'                                               */
+    int device;             /* CUDA device ordinal holding the table                */
+    uint64_t *d_table;      /* device: n_buckets x 4 x u64, empty slot = ~0         */
+    uint32_t n_buckets;     /* 32-byte buckets                                      */
+    uint32_t has_all_ones;  /* key 2^64-1 (k=32 poly-T) stored out of band          */
+    uint64_t n_distinct;    /* distinct keys resident in the table                  */
+    double build_ms;        /* device time of parse+insert                          */
+} hash_set;
+
+/* ------------------------------------------------------------------------
+ * (1) Legacy symbols -- drop-in for c/kmers.c
+ * ---------------------------------------------------------------------- */
+
+/* Replaces create_kmer_hash_set, c/kmers.c:185-229 (+ peek_at_file :124-146,
+ * initialize_hash_set :160-180, add_to_hash :112-122): k = length of the first
+ * line, num_kmers = number of lines, keys inserted RAW (not canonicalised) by
+ * the sm_100a insert kernel.  Uses the current tb device (default 0). */
+hash_set *create_kmer_hash_set(char *kmer_file_path);
+
+/* Replaces count_kmers_in_read, c/kmers.c:270-299 (+ kmer_in_hash_set :245-268):
+ * a batch of one read through the CUDA classify kernel. */
+void count_kmers_in_read(char *read, hash_set *haplotype_A, hash_set *haplotype_B,
+                         int *count_A, int *count_B);
+
+/* Replaces kmer_to_int, c/kmers.c:50-72 (string utility; host arithmetic). */
+uint64_t kmer_to_int(char *kmer, unsigned char k);
+
+/* Replaces reverse_complement, c/kmers.c:74-93 (non-ACGT positions of `out`
+ * are left untouched, as in the reference). */
+void reverse_complement(char *kmer_in, char *kmer_out, unsigned char k);
+
+/* Replaces hash_function, c/kmers.c:98-103.  Kept for API completeness; the
+ * device table uses its own hash (membership does not depend on layout). */
+unsigned int hash_function(uint64_t x);
+
+/* Replaces kmer_in_hash_set, c/kmers.c:245-268, for one k-mer string: canonical
+ * min(fwd, revcomp) lookup in the device table.  `empty_kmer_buffer` receives
+ * the reverse complement like the reference's scratch buffer. */
+char kmer_in_hash_set(char *kmer, char *empty_kmer_buffer, hash_set *set);
+
+/* ------------------------------------------------------------------------
+ * (2) B200 API
+ * ---------------------------------------------------------------------- */
+
+const char *tb_last_error(void);
+const char *tb_version(void);
+
+/* Devices.  One process per GPU is the intended model (tb_set_device once). */
+int tb_device_count(void);
+int tb_set_device(int device);
+int tb_get_device(void);
+/* name into buf; sm count, HBM bytes, L2 bytes returned through pointers (may be NULL) */
+int tb_device_info(int device, char *name_buf, int name_len, int *sm_count,
+                   uint64_t *hbm_bytes, uint64_t *l2_bytes);
+
+/* Pinned host memory for batch buffers. */
+void *tb_host_alloc(uint64_t bytes);
+void tb_host_free(void *p);
+
+/* Sets. */
+hash_set *tb_set_create_from_file(const char *path, int device);
+/* keys: RAW LSB-first 2-bit encodings (c/kmers.c:50-72) in host memory;
+ * num_kmers := n (as if the file had n lines). */
+hash_set *tb_set_create_from_keys(const uint64_t *keys, uint64_t n, int k, int device);
+void tb_set_destroy(hash_set *s);
+/* membership of already-encoded lookup keys (host arrays), for tests */
+int tb_set_contains_keys(const hash_set *s, const uint64_t *keys, uint64_t n, unsigned char *out);
+/* load factor used for new tables (slots = 4*n_buckets); default 0.5, (0,0.95] */
+int tb_set_load_factor(double lf);
+
+/* Scaling factors, classify_by_kmers.py:57-77 (fp64). */
+void tb_scaling_factors(const hash_set *A, const hash_set *B, double *scale_A, double *scale_B);
+
+/* One-shot batch: reads are concatenated ASCII in `bases` (host memory, pinned or
+ * pageable), read r = bases[offsets[r] .. offsets[r+1]); offsets has n_reads+1
+ * entries.  Outputs are host arrays of n_reads entries; score_* and bin may be
+ * NULL.  bin[r] in {'A','B','U'} (classify_by_kmers.py:104-115, on device, fp64).
+ * Per read this equals count_kmers_in_read + the driver's decision. */
+int tb_classify_batch(const char *bases, const int64_t *offsets, int64_t n_reads,
+                      const hash_set *A, const hash_set *B,
+                      int32_t *count_A, int32_t *count_B,
+                      double *score_A, double *score_B, char *bin);
+
+/* Double-buffered asynchronous classifier: `n_slots` independent slots, each with
+ * its own CUDA stream and device buffers for up to max_bases / max_reads per
+ * batch.  submit() enqueues H2D copy + pack + classify + decide + D2H copy on
+ * the slot's stream and returns; wait() blocks until that slot's results are in
+ * the host arrays given to submit().  Host buffers should come from
+ * tb_host_alloc for true asynchrony. */
+typedef struct tb_classifier tb_classifier;
+tb_classifier *tb_classifier_create(const hash_set *A, const hash_set *B,
+                                    int64_t max_bases, int64_t max_reads, int n_slots);
+void tb_classifier_destroy(tb_classifier *c);
+int tb_classifier_submit(tb_classifier *c, int slot,
+                         const char *bases, const int64_t *offsets, int64_t n_reads,
+                         int32_t *count_A, int32_t *count_B,
+                         double *score_A, double *score_B, char *bin);
+int tb_classifier_wait(tb_classifier *c, int slot);
+/* Timing marks: record CUDA event `which` (0 or 1) on the slot's stream at the
+ * current point of its queue; elapsed() waits for the `to` mark and returns the
+ * device time between two marks (possibly of different slots) in milliseconds. */
+int tb_classifier_mark(tb_classifier *c, int slot, int which);
+int tb_classifier_elapsed(tb_classifier *c, int slot_from, int which_from, int slot_to,
+                          int which_to, float *ms);
+/* Re-run the device part (pack + classify + decide; no copies) of the batch last
+ * submitted to `slot`, `iters` times, timed with CUDA events on the slot's
+ * stream.  Returns total milliseconds in *ms_total and the classify kernel's
+ * share in *ms_classify (measured with its own event pair).  Used by bench.py
+ * for the HBM-resident figure and the roofline. */
+int tb_classifier_rerun_resident(tb_classifier *c, int slot, int iters,
+                                 float *ms_total, float *ms_classify);
+/* Counters of the last batch in a slot: windows, probes as the reference performs
+ * them (W + (W - hits_A)), reads that took the Q3-UB fix-up path. */
+int tb_classifier_stats(tb_classifier *c, int slot, uint64_t *n_windows,
+                        uint64_t *n_probes, uint64_t *n_fixup_reads, uint64_t *n_kernel_launches);
+
+/* Random-32-byte-sector gather microbenchmark (roofline denominator):
+ * every thread issues `loads_in_flight` independent 32-B loads per step at
+ * pseudo-random sector addresses of a `table_bytes` buffer.  Returns sectors/s. */
+int tb_gather_bench(uint64_t table_bytes, int loads_in_flight, int threads_per_block,
+                    int blocks_per_sm, int steps, int variant,
+                    double *sectors_per_s, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRIO_KMERS_B200_H */

@@ -1,0 +1,391 @@
+"""Parity of the CUDA path (through the C ABI / the Python boundary) with the
+oracle and the committed golden vectors.  Bit-exact: counts, bins; scores are
+IEEE fp64 products and must be equal (tolerance stated where used: 1e-12 rel).
+
+Mirrors reference tests/test_kmers.py and tests/test_classify_by_kmers.py, then
+adds the cases the reference does not pin: non-ACGT handling,
+unfindable k-mers, k != 21, ragged/duplicate set files, empty and tiny reads,
+batch-shape independence, and full-size (BASELINE configs[1]) properties.
+"""
+import gzip
+import hashlib
+import os
+from unittest.mock import patch
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, REF_DATA
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kmers():
+    from trio_binning_b200 import kmers as mod
+
+    assert mod.device_count() > 0, "GPU tests need a CUDA device"
+    return mod
+
+
+@pytest.fixture(scope="module")
+def fixture_sets(kmers):
+    a = kmers.create_kmer_hash_set(os.path.join(REF_DATA, "hapA.txt"))
+    b = kmers.create_kmer_hash_set(os.path.join(REF_DATA, "hapB.txt"))
+    return a, b
+
+
+# ---------------------------------------------------------------- reference tests
+def test_build_kmer_hash(kmers):  # reference tests/test_kmers.py:8-11
+    s = kmers.create_kmer_hash_set(os.path.join(REF_DATA, "hapA.txt"))
+    assert kmers.get_number_kmers_in_set(s) == 4
+    assert s.contents.k == 21 and s.contents.hash_size == 5
+    assert s.contents.n_distinct == 4
+
+
+def test_count_kmers_in_read(kmers, fixture_sets):  # reference tests/test_kmers.py:14-25
+    a, b = fixture_sets
+    assert kmers.count_kmers_in_read(
+        "CTTATCATGTCTTTGTTTTCAAAGCTTCTTAGAGGTTTTTTTTTTTGGTGTTAATTGGCATAAATTATGGCT", a, b) == (2, 1)
+
+
+@pytest.mark.parametrize("kmer_str,kmer_int", [
+    ("ATGCTAGCTAGAGAGAGAGGA", 696357446508),
+    ("TTTTTTTTTTTTTTTTTTTTTTTTTTTT", 72057594037927935),
+    ("TTTTTTTTTTTTTTTAGGCCCACTTTTT", 72006304612220927),
+    ("AAAAAAAAAAAAAAAAAAAAAAAAAA", 0),
+    ("GGGAGGGAGGGAGGGAGGGAGGGAGGG", 11868309606246954),
+])
+def test_kmer_to_int(kmers, kmer_str, kmer_int):  # reference tests/test_kmers.py:28-39
+    assert kmers.kmer_to_int(kmer_str) == kmer_int
+
+
+@pytest.mark.parametrize("kmer,revcomp_kmer", [
+    ("ATGCTAGCTAGAGAGAGAGGA", "TCCTCTCTCTCTAGCTAGCAT"),
+    ("TTTTTTTTTTTTTTTTTTTTTTTTTTTT", "AAAAAAAAAAAAAAAAAAAAAAAAAAAA"),
+    ("TTTTTTTTTTTTTTTAGGCCCACTTTTT", "AAAAAGTGGGCCTAAAAAAAAAAAAAAA"),
+    ("AAAAAAAAAAAAAAAAAAAAAAAAAA", "TTTTTTTTTTTTTTTTTTTTTTTTTT"),
+    ("GGGAGGGAGGGAGGGAGGGAGGGAGGG", "CCCTCCCTCCCTCCCTCCCTCCCTCCC"),
+])
+def test_reverse_complement(kmers, kmer, revcomp_kmer):  # reference tests/test_kmers.py:42-53
+    assert kmers.reverse_complement(kmer) == revcomp_kmer
+
+
+def test_classify_by_kmers_help(capsys):  # reference tests/test_classify_by_kmers.py:10-16
+    from trio_binning_b200.classify_by_kmers import main
+
+    with patch("sys.argv", ["classify-by-kmers", "--help"]):
+        with pytest.raises(SystemExit):
+            main()
+    out, _ = capsys.readouterr()
+    assert "Classify reads into bins" in out
+
+
+def _run_cli(tmpdir, reads, extra=()):
+    from trio_binning_b200.classify_by_kmers import main
+
+    argv = ["classify-by-kmers", reads, os.path.join(REF_DATA, "hapA.txt"), os.path.join(REF_DATA, "hapB.txt"),
+            "--haplotype-a-out-prefix", os.path.join(tmpdir, "hapA"),
+            "--haplotype-b-out-prefix", os.path.join(tmpdir, "hapB"),
+            "--unclassified-out-prefix", os.path.join(tmpdir, "hapU")] + list(extra)
+    with patch("sys.argv", argv):
+        main()
+
+
+def test_classify_by_kmers_cli_plain(capsys, tmpdir, golden_cli):
+    """reference tests/test_classify_by_kmers.py:19-57, plus the TSV and the exact
+    bytes of both files (the reference's overlap-bug artefact included)."""
+    from trio_binning_b200.seq import readfq
+
+    _run_cli(str(tmpdir), os.path.join(REF_DATA, "test.ccs.fastq.gz"), ["--no-gzip-output"])
+    out, _ = capsys.readouterr()
+    assert out == golden_cli["plain"]["stdout"]
+    hap_a_out = readfq(open(os.path.join(tmpdir, "hapA.fastq"), "r"))
+    correct_out = readfq(open(os.path.join(REF_DATA, "hapA.fastq"), "r"))
+    num_reads = 0
+    for seq1, seq2 in zip(hap_a_out, correct_out):
+        num_reads += 1
+        assert seq1.name == seq2.name
+        assert seq1.seq == seq2.seq
+        assert seq1.qual == seq2.qual
+    assert num_reads == 1
+    assert sorted(os.listdir(tmpdir)) == sorted(golden_cli["plain"]["files"])
+    for name, meta in golden_cli["plain"]["files"].items():
+        raw = open(os.path.join(tmpdir, name), "rb").read()
+        assert hashlib.sha256(raw).hexdigest() == meta["sha256"], name
+    assert open(os.path.join(tmpdir, "hapA.fastq"), "rb").read() == open(os.path.join(REF_DATA, "hapA.fastq"), "rb").read()
+
+
+def test_classify_by_kmers_cli_gz(capsys, tmpdir, golden_cli):
+    _run_cli(str(tmpdir), os.path.join(REF_DATA, "test.ccs.fastq.gz"))
+    out, _ = capsys.readouterr()
+    assert out == golden_cli["gz"]["stdout"]
+    assert sorted(os.listdir(tmpdir)) == sorted(golden_cli["gz"]["files"])
+    for name, meta in golden_cli["gz"]["files"].items():
+        raw = gzip.decompress(open(os.path.join(tmpdir, name), "rb").read())
+        assert hashlib.sha256(raw).hexdigest() == meta["sha256"], name
+
+
+@pytest.mark.parametrize("name", ["test.fa", "test.fastq"])
+def test_classify_by_kmers_cli_other_inputs(capsys, tmpdir, golden_cli, name):
+    _run_cli(str(tmpdir), os.path.join(REF_DATA, name), ["--batch-bases", "50"])
+    out, _ = capsys.readouterr()
+    assert out == golden_cli[name]["stdout"]
+    for fn, text in golden_cli[name]["files_text"].items():
+        assert gzip.decompress(open(os.path.join(tmpdir, fn), "rb").read()).decode() == text
+
+
+# ---------------------------------------------------------------- golden vectors
+def test_golden_counts(kmers, golden_counts):
+    """Vectors from the compiled reference: unmodified (non-ACGT only at positions
+    >= k) and zero-initialised scratch (non-ACGT anywhere: the Q3-UB contract)."""
+    for case in golden_counts:
+        a = kmers.create_kmer_hash_set(os.path.join(GOLDEN, case["set_a"]))
+        b = kmers.create_kmer_hash_set(os.path.join(GOLDEN, case["set_b"]))
+        assert kmers.get_number_kmers_in_set(a) == case["num_kmers_a"]
+        assert kmers.get_number_kmers_in_set(b) == case["num_kmers_b"]
+        assert a.contents.k == case["k"]
+        got = [list(c) for c in kmers.count_kmers_in_reads(case["reads"], a, b)]
+        bad = [i for i, (g, w) in enumerate(zip(got, case["counts"])) if g != w]
+        assert not bad, (case["name"], bad[:5], [got[i] for i in bad[:5]], [case["counts"][i] for i in bad[:5]])
+        # the per-read legacy entry point gives the same numbers (batch of one)
+        for i in range(0, len(case["reads"]), 7):
+            assert list(kmers.count_kmers_in_read(case["reads"][i], a, b)) == case["counts"][i]
+        kmers.destroy_kmer_hash_set(a)
+        kmers.destroy_kmer_hash_set(b)
+
+
+def test_golden_decisions_and_scores(kmers, oracle, golden_counts):
+    case = golden_counts[0]
+    a = kmers.create_kmer_hash_set(os.path.join(GOLDEN, case["set_a"]))
+    b = kmers.create_kmer_hash_set(os.path.join(GOLDEN, case["set_b"]))
+    res = kmers.classify_reads(case["reads"], a, b)
+    sa, sb = oracle.scaling_factors(case["num_kmers_a"], case["num_kmers_b"])
+    assert kmers.scaling_factors(a, b) == (sa, sb)  # fp64, bit-equal (<= 1e-12 rel required)
+    counts = np.array(case["counts"], dtype=np.int32)
+    wa, wb, wbin = oracle.decide(counts[:, 0], counts[:, 1], sa, sb)
+    for i, (ca, cb, xa, xb, bn) in enumerate(res):
+        assert [ca, cb] == case["counts"][i]
+        assert xa == wa[i] and xb == wb[i]
+        assert bn == chr(wbin[i])
+
+
+# ---------------------------------------------------------------- randomised vs oracle
+def _oracle_sets(oracle, keys_a, keys_b, k):
+    return oracle.set_from_ints(keys_a, k), oracle.set_from_ints(keys_b, k)
+
+
+@pytest.mark.parametrize("k,n_keys,mean_len,n_reads,fixed", [
+    (21, 20000, 3000, 300, False),
+    (31, 20000, 3000, 300, False),
+    (32, 5000, 1000, 200, False),
+    (21, 20000, 150, 4000, True),      # short-read shape (configs[4])
+    (15, 3000, 500, 500, False),
+    (1, 1, 200, 50, False),
+    (2, 5, 200, 50, False),
+])
+def test_random_batches_vs_oracle(kmers, oracle, k, n_keys, mean_len, n_reads, fixed):
+    from trio_binning_b200 import synth
+
+    ka, kb = synth.random_kmer_sets(n_keys, n_keys // 2 + 1, k, seed=k * 7 + 1)
+    bases, offsets, _ = synth.random_reads(n_reads, mean_len, k, ka, kb, seed=k, plant_every=200,
+                                           fixed_len=fixed, invalid_rate=0.002)
+    A = kmers.create_kmer_hash_set_from_ints(ka, k)
+    B = kmers.create_kmer_hash_set_from_ints(kb, k)
+    oa, ob = _oracle_sets(oracle, ka, kb, k)
+    ca, cb, sa, sb, bins = kmers.classify_packed(bases, offsets, A, B)
+    wa, wb = oracle.count_batch(bases, offsets, oa, ob)
+    assert (ca == wa).all() and (cb == wb).all(), np.nonzero((ca != wa) | (cb != wb))[0][:10]
+    if k > 2:
+        assert wa.sum() > 0 and wb.sum() > 0  # the workload does exercise hits
+    fa, fb = oracle.scaling_factors(len(ka), len(kb))
+    xa, xb, xbin = oracle.decide(wa, wb, fa, fb)
+    assert (sa == xa).all() and (sb == xb).all() and (bins == xbin).all()
+    oracle.set_free(oa)
+    oracle.set_free(ob)
+    kmers.destroy_kmer_hash_set(A)
+    kmers.destroy_kmer_hash_set(B)
+
+
+def test_invalid_bases_everywhere_vs_oracle(kmers, oracle):
+    """Non-ACGT bytes anywhere (incl. the first k bases -> fix-up kernel), long N runs,
+    reads that are all N, lowercase, CR, and bytes >= 0x80."""
+    from trio_binning_b200 import synth
+
+    k = 21
+    ka, kb = synth.random_kmer_sets(3000, 3000, k, seed=5)
+    rng = np.random.default_rng(11)
+    bases, offsets, _ = synth.random_reads(600, 400, k, ka, kb, seed=3, plant_every=60)
+    bases = bases.copy()
+    junk = np.frombuffer(b"NnacgtRY\r\x80\xff-", dtype=np.uint8)
+    pos = rng.integers(0, len(bases), size=len(bases) // 25)
+    bases[pos] = junk[rng.integers(0, len(junk), size=len(pos))]
+    for r in range(0, 600, 9):  # N runs of assorted lengths at assorted places, some at read start
+        s, e = offsets[r], offsets[r + 1]
+        a = s if r % 2 else s + int(rng.integers(0, max(1, e - s)))
+        bases[a:min(e, a + int(rng.integers(1, 120)))] = ord("N")
+    bases[offsets[10]:offsets[11]] = ord("N")  # a read with no valid base at all
+    A = kmers.create_kmer_hash_set_from_ints(ka, k)
+    B = kmers.create_kmer_hash_set_from_ints(kb, k)
+    oa, ob = _oracle_sets(oracle, ka, kb, k)
+    ca, cb, *_ = kmers.classify_packed(bases, offsets, A, B)
+    wa, wb = oracle.count_batch(bases, offsets, oa, ob)
+    bad = np.nonzero((ca != wa) | (cb != wb))[0]
+    assert len(bad) == 0, (bad[:10], ca[bad[:10]], wa[bad[:10]], cb[bad[:10]], wb[bad[:10]])
+    assert wa.sum() > 100 and wb.sum() > 100
+
+
+def test_edge_shapes(kmers, oracle, fixture_sets):
+    a, b = fixture_sets
+    oa = oracle.set_from_file(os.path.join(REF_DATA, "hapA.txt"))
+    ob = oracle.set_from_file(os.path.join(REF_DATA, "hapB.txt"))
+    hit = "CTTATCATGTCTTTGTTTTCAAAGCTTCTTAGAGGTTTTTTTTTTTGGTGTTAATTGGCATAAATTATGGCT"
+    reads = ["", "A", "ACGT" * 5, hit[:21], hit[:20], hit, "", "", hit * 40, "N" * 100, hit[::-1], "",
+             "n" + hit, hit + "N", "ACGTN" * 300]
+    got = kmers.count_kmers_in_reads(reads, a, b)
+    want = [oracle.count(r, oa, ob) for r in reads]
+    assert got == want
+    # empty batch, batch of only empty reads
+    assert kmers.count_kmers_in_reads([], a, b) == []
+    assert kmers.count_kmers_in_reads(["", ""], a, b) == [(0, 0), (0, 0)]
+    # NUL byte cuts the read like strlen does (c/kmers.c:285); non-ASCII is UTF-8 bytes
+    assert kmers.count_kmers_in_reads([hit + "\x00" + hit], a, b) == [oracle.count(hit, oa, ob)]
+    assert kmers.count_kmers_in_reads(["é" + hit], a, b) == [oracle.count(("é" + hit).encode(), oa, ob)]
+
+
+def test_batch_shape_independence(kmers):
+    """Same reads, different batch compositions and orders -> same per-read result."""
+    from trio_binning_b200 import synth
+
+    k = 21
+    ka, kb = synth.random_kmer_sets(5000, 5000, k, seed=9)
+    bases, offsets, _ = synth.random_reads(257, 1500, k, ka, kb, seed=4, plant_every=100, invalid_rate=0.001)
+    A = kmers.create_kmer_hash_set_from_ints(ka, k)
+    B = kmers.create_kmer_hash_set_from_ints(kb, k)
+    ca, cb, *_ = kmers.classify_packed(bases, offsets, A, B)
+    reads = [bytes(bases[offsets[i]:offsets[i + 1]]).decode("latin-1") for i in range(257)]
+    one_by_one = [kmers.count_kmers_in_read(r, A, B) for r in reads[:40]]
+    assert one_by_one == list(zip(ca[:40].tolist(), cb[:40].tolist()))
+    perm = np.random.default_rng(0).permutation(257)
+    shuffled = kmers.count_kmers_in_reads([reads[i] for i in perm], A, B)
+    assert shuffled == [(int(ca[i]), int(cb[i])) for i in perm]
+    with kmers.Classifier(A, B, max_bases=int(offsets[-1]), max_reads=257, n_slots=2) as clf:
+        half = 128
+        clf.submit(0, bases[:offsets[half]], offsets[:half + 1])
+        clf.submit(1, bases[offsets[half]:], offsets[half:] - offsets[half])
+        r0, r1 = clf.result(0), clf.result(1)
+        assert (np.concatenate([r0[0], r1[0]]) == ca).all()
+        assert (np.concatenate([r0[1], r1[1]]) == cb).all()
+        st = clf.stats(0)
+        assert st["windows"] == synth.total_windows(offsets[:half + 1], k)
+        assert st["probes"] == 2 * st["windows"] - int(ca[:half].sum())
+
+
+# ---------------------------------------------------------------- set loader
+def test_set_file_quirks(kmers, oracle, tmp_path):
+    """Q1 (raw insert), Q5 (duplicates counted, ragged lines, missing final newline),
+    k = 32 all-T (the table's empty sentinel), membership vs the oracle's table."""
+    rng = np.random.default_rng(2)
+    k = 32
+    lines = ["".join("ACGT"[i] for i in rng.integers(0, 4, k)) for _ in range(500)]
+    lines += lines[:20] + ["T" * 32, "A" * 32]
+    p = tmp_path / "k32.txt"
+    p.write_text("\n".join(lines))  # no final newline
+    s = kmers.create_kmer_hash_set(str(p))
+    o = oracle.set_from_file(str(p))
+    assert kmers.get_number_kmers_in_set(s) == o.contents.num_kmers == 522
+    assert s.contents.n_distinct + s.contents.has_all_ones == 502
+    probe = np.array([oracle.kmer_to_int(x) for x in lines] + [int(x) for x in rng.integers(0, 2**63, 2000)],
+                     dtype=np.uint64)
+    want = np.array([oracle.contains(o, int(x)) for x in probe])
+    assert (kmers.set_contains_ints(s, probe) == want).all()
+    assert want[:522].all()
+
+    ragged = tmp_path / "ragged.txt"
+    ragged.write_text("ACCTCTAAGAAGCTTTGAAAA\nCTTAT\n\nCCAGCTGTGTGATTGGTCCGC\nGG")
+    s2, o2 = kmers.create_kmer_hash_set(str(ragged)), oracle.set_from_file(str(ragged))
+    assert kmers.get_number_kmers_in_set(s2) == o2.contents.num_kmers == 5
+    n = o2.contents.hash_size
+    stored = np.ctypeslib.as_array(o2.contents.kmers, (n,))[np.ctypeslib.as_array(o2.contents.full, (n,)) == 1]
+    assert kmers.set_contains_ints(s2, stored).all()
+
+    lower = tmp_path / "lower.txt"
+    lower.write_text("acgtacgtacgtacgtacgta\nACGTNACGTACGTACGTACGT\n")
+    s3, o3 = kmers.create_kmer_hash_set(str(lower)), oracle.set_from_file(str(lower))
+    n = o3.contents.hash_size
+    stored = np.ctypeslib.as_array(o3.contents.kmers, (n,))[np.ctypeslib.as_array(o3.contents.full, (n,)) == 1]
+    assert kmers.set_contains_ints(s3, stored).all()
+
+    for bad in ("", "\n", "A" * 40 + "\n"):
+        q = tmp_path / "bad.txt"
+        q.write_text(bad)
+        with pytest.raises(RuntimeError):
+            kmers.create_kmer_hash_set(str(q))
+
+
+def test_degenerate_tiny_sets_terminate(kmers, tmp_path):
+    # Q6: 1- and 2-line files make the reference spin forever on a miss; we terminate
+    p = tmp_path / "one.txt"
+    p.write_text("ACGTACGTACGTACGTACGTA\n")
+    s = kmers.create_kmer_hash_set(str(p))
+    assert kmers.count_kmers_in_read("ACGTACGTACGTACGTACGTAGGGGGGGGGGGGGGGGGGGGGGGGG", s, s) == (1, 0)
+
+
+def test_mismatched_k_is_an_error(kmers, fixture_sets, tmp_path):
+    p = tmp_path / "k5.txt"
+    p.write_text("ACGTA\nCCCCC\nGGGGA\n")
+    s5 = kmers.create_kmer_hash_set(str(p))
+    with pytest.raises(RuntimeError, match="k differs"):
+        kmers.count_kmers_in_reads(["ACGTACGTACGT"], fixture_sets[0], s5)
+
+
+# ---------------------------------------------------------------- full size (configs[1])
+def test_config2_full_size_properties(kmers, oracle, tmp_path_factory):
+    """BASELINE configs[1]: 10k reads (mean 20 kb) vs 10M + 10M 21-mers, through the
+    text loader.  Checked by (1) the oracle on a deterministic subsample of reads,
+    (2) reverse-complement symmetry on all-ACGT reads (the multiset of canonical
+    keys of a read and of its reverse complement are equal), (3) additivity:
+    a read cut into pieces overlapping by k-1 bases has the counts of the whole."""
+    from trio_binning_b200 import synth
+
+    k, n = 21, 10_000_000
+    tmp = str(tmp_path_factory.mktemp("c2"))
+    ka, kb, pa, pb = synth.materialise_sets(tmp, n, n, k, seed=42)
+    A = kmers.create_kmer_hash_set(pa)
+    B = kmers.create_kmer_hash_set(pb)
+    assert kmers.get_number_kmers_in_set(A) == n and A.contents.n_distinct == n
+    bases, offsets, hap = synth.random_reads(10_000, 20_000, k, ka, kb, seed=43, plant_every=1000)
+    ca, cb, sa, sb, bins = kmers.classify_packed(bases, offsets, A, B)
+    # planted haplotype wins (findable plants only: about half of them, quirk Q1)
+    assert (bins[hap == 0] == ord("A")).mean() > 0.97
+    assert (bins[hap == 1] == ord("B")).mean() > 0.97
+    # (1) oracle on every 50th read
+    oa, ob = oracle.set_from_ints(ka, k), oracle.set_from_ints(kb, k)
+    for r in range(0, 10_000, 50):
+        assert oracle.count(bytes(bases[offsets[r]:offsets[r + 1]]), oa, ob) == (ca[r], cb[r]), r
+    # (2) reverse complement of the whole batch, read by read
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[np.frombuffer(b"ACGT", dtype=np.uint8)] = np.frombuffer(b"TGCA", dtype=np.uint8)
+    sub = slice(0, 2000)
+    sub_off = offsets[: 2001]
+    rc = np.empty(int(sub_off[-1]), dtype=np.uint8)
+    for r in range(2000):
+        rc[sub_off[r]:sub_off[r + 1]] = comp[bases[sub_off[r]:sub_off[r + 1]][::-1]]
+    ra, rb, *_ = kmers.classify_packed(rc, sub_off, A, B)
+    assert (ra == ca[sub]).all() and (rb == cb[sub]).all()
+    # (3) additivity over chunks overlapping by k-1
+    piece = 1000
+    starts, lens, owner = [], [], []
+    for r in range(500):
+        s, e = int(offsets[r]), int(offsets[r + 1])
+        for p in range(s, max(s + 1, e - (k - 1)), piece):
+            starts.append(p)
+            lens.append(min(e, p + piece + k - 1) - p)
+            owner.append(r)
+    poff = np.zeros(len(starts) + 1, dtype=np.int64)
+    np.cumsum(lens, out=poff[1:])
+    pbases = np.concatenate([bases[s:s + n_] for s, n_ in zip(starts, lens)])
+    pa_, pb_, *_ = kmers.classify_packed(pbases, poff, A, B)
+    owner = np.array(owner)
+    assert (np.bincount(owner, weights=pa_, minlength=500) == ca[:500]).all()
+    assert (np.bincount(owner, weights=pb_, minlength=500) == cb[:500]).all()

@@ -1,0 +1,463 @@
+// classify.cu -- the classify-by-kmers hot path on sm_100a.
+//
+// Replaces, for a whole batch of reads per launch:
+//   count_kmers_in_read   c/kmers.c:270-299   (window loop, A then else-B)
+//   kmer_in_hash_set      c/kmers.c:245-268   (encode fwd + revcomp, min, probe)
+//   kmer_to_int           c/kmers.c:50-72     (2-bit LSB-first encode)
+//   reverse_complement    c/kmers.c:74-93     (incl. the "no write for non-ACGT" quirk Q3)
+//   score + decision      classify_by_kmers.py:104-115 (fp64, on device)
+//
+// Formulation (validated on the CPU in oracle/oracle.py::window_keys): with
+//   F[x] = code(read[x]), non-ACGT -> 0
+//   E[x] = code of the nearest ACGT base at or before x            (fill-forward)
+// window i of a read has   fwd = sum_j F[i+j] << 2j,
+//                          rc  = sum_j (3-E[i+j]) << 2(k-1-j),   key = min(fwd, rc)
+// for every window except the first skip[r] windows of a read whose first k
+// bases contain a non-ACGT byte (the reference reads never-written scratch
+// there, Q3-UB); those few windows are done literally by k_fixup.
+// Windows are therefore independent: the batch is ONE flat 2-bit stream cut
+// into tiles of 1024 window-start positions, one warp per tile, one lane per
+// 32 consecutive positions (= one aligned 64-bit word of the stream), whatever
+// the read lengths are.
+#include "launchers.h"
+
+namespace {
+
+// ============================================================================
+// k_pack: flat ASCII -> F words, dirty bitmap, sparse E words, Q3-UB flags.
+// One thread per 32-base word; a warp covers one tile, so the dirty bitmap word
+// of the tile is a single ballot.
+// ============================================================================
+
+__device__ __forceinline__ uint32_t valid_mask4(uint32_t x)
+{
+    // 0xFF in every byte of x that is one of 'A','C','G','T'
+    return __vcmpeq4(x, 0x41414141u) | __vcmpeq4(x, 0x43434343u) | __vcmpeq4(x, 0x47474747u) |
+           __vcmpeq4(x, 0x54545454u);
+}
+
+// 4 ASCII bytes -> 8 bits of codes (byte i -> bits 2i) and 4 validity bits
+__device__ __forceinline__ void pack4(uint32_t x, uint32_t &codes, uint32_t &valid)
+{
+    uint32_t vm = valid_mask4(x);
+    uint32_t t = ((x >> 1) ^ (x >> 2)) & 0x03030303u & vm;
+    codes = (t | (t >> 6) | (t >> 12) | (t >> 18)) & 0xFFu;
+    uint32_t v = vm & 0x01010101u;
+    valid = (v | (v >> 7) | (v >> 14) | (v >> 21)) & 0xFu;
+}
+
+// read that contains flat position x (offsets non-decreasing, offsets[n]=total > x)
+__device__ __forceinline__ int64_t read_of_position(const int64_t *__restrict__ offsets,
+                                                     int64_t n_reads, int64_t x)
+{
+    int64_t lo = 0, hi = n_reads;  // invariant: offsets[lo] <= x < offsets[hi]
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// code of the nearest valid base strictly before flat position x (0 if none)
+__device__ __noinline__ uint32_t lookback_code(const unsigned char *__restrict__ ascii, int64_t x)
+{
+    int64_t p = x - 1;
+    // byte-wise down to a 16-byte boundary, then 16 bytes at a time
+    while (p >= 0 && ((p + 1) & 15)) {
+        unsigned char c = ascii[p];
+        if (tb_base_valid(c)) return tb_base_code(c);
+        p--;
+    }
+    while (p >= 15) {
+        uint4 q = *reinterpret_cast<const uint4 *>(ascii + p - 15);
+        if (valid_mask4(q.x) | valid_mask4(q.y) | valid_mask4(q.z) | valid_mask4(q.w)) break;
+        p -= 16;
+    }
+    while (p >= 0) {
+        unsigned char c = ascii[p];
+        if (tb_base_valid(c)) return tb_base_code(c);
+        p--;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_pack(tb_batch_view b, int k)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // word index
+    const int64_t p0 = w * 32;
+    uint64_t f = 0;
+    uint32_t vmask = 0xFFFFFFFFu;  // positions past the end count as valid 'A'
+    if (p0 + 32 <= b.total_bases) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(b.ascii + p0);
+        uint4 q0 = __ldg(src), q1 = __ldg(src + 1);
+        uint32_t x[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+        vmask = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t c, v;
+            pack4(x[i], c, v);
+            f |= (uint64_t)c << (8 * i);
+            vmask |= v << (4 * i);
+        }
+    } else if (p0 < b.total_bases) {
+        int n = (int)(b.total_bases - p0);
+        for (int i = 0; i < n; i++) {
+            unsigned char c = b.ascii[p0 + i];
+            if (tb_base_valid(c))
+                f |= (uint64_t)tb_base_code(c) << (2 * i);
+            else
+                vmask &= ~(1u << i);
+        }
+    }
+    b.F[w] = f;
+    const bool is_dirty = vmask != 0xFFFFFFFFu;
+    if (is_dirty) {
+        // rare path: fill-forward stream + Q3-UB flagging
+        uint32_t carry = lookback_code(b.ascii, p0);
+        uint64_t e = 0;
+        int64_t r = -1, r_end = -1, r_start = 0;
+        for (int i = 0; i < 32; i++) {
+            if ((vmask >> i) & 1u) {
+                carry = (uint32_t)(f >> (2 * i)) & 3u;
+            } else {
+                int64_t x = p0 + i;
+                if (x >= r_end) {
+                    r = read_of_position(b.offsets, b.n_reads, x);
+                    r_start = b.offsets[r];
+                    r_end = b.offsets[r + 1];
+                }
+                if (x - r_start < k) atomicOr(&b.flags[r], 2u);
+            }
+            e |= (uint64_t)carry << (2 * i);
+        }
+        b.E[w] = e;
+    }
+    unsigned d = __ballot_sync(0xFFFFFFFFu, is_dirty);
+    if ((threadIdx.x & 31) == 0) b.dirty[w >> 5] = d;
+}
+
+// ============================================================================
+// k_index: one thread per read.  tile -> first read map, zero the counts, and
+// for Q3-UB-flagged reads compute how many leading windows the fix-up kernel
+// must redo:  U[j] = (first ACGT position >= j) - j  for slot j < k,
+// skip = min(max_j U[j], windows).
+// ============================================================================
+__global__ void __launch_bounds__(256)
+k_index(tb_batch_view b, int k)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= b.n_reads) return;
+    const int64_t start = b.offsets[r], end = b.offsets[r + 1];
+    for (int64_t t = (start + 1023) >> 10; (t << 10) < end; t++)
+        b.tile_first_read[t] = (uint32_t)r;
+    b.count_a[r] = 0;
+    b.count_b[r] = 0;
+    uint32_t skip = 0;
+    if (b.flags[r] & 2u) {
+        b.flags[r] = 0;
+        const int64_t len = end - start;
+        const int64_t windows = len - k + 1;
+        if (windows > 0) {
+            int64_t max_u = 0;
+            int64_t p = 0;  // first valid position >= j is non-decreasing in j
+            for (int j = 0; j < k; j++) {
+                if (p < j) p = j;
+                while (p < len && !tb_base_valid(b.ascii[start + p])) p++;
+                if (p - j > max_u) max_u = p - j;
+            }
+            skip = (uint32_t)(max_u < windows ? max_u : windows);
+            if (skip) b.ub_list[atomicAdd(b.ub_count, 1u)] = (uint32_t)r;
+        }
+    }
+    b.skip[r] = skip;
+}
+
+// ============================================================================
+// k_classify
+// ============================================================================
+
+// bits [shift, shift+64) of the 128-bit value hi:lo  (0 <= shift < 128)
+__device__ __forceinline__ uint64_t extract128(uint64_t lo, uint64_t hi, int shift)
+{
+    if (shift >= 64) return hi >> (shift - 64);
+    if (shift == 0) return lo;
+    return (lo >> shift) | (hi << (64 - shift));
+}
+
+template <int K, int U>
+__global__ void __launch_bounds__(128)
+k_classify(tb_batch_view b, int k_runtime, tb_set_view A, tb_set_view B)
+{
+    const int k = K ? K : k_runtime;
+    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= b.n_tiles) return;  // warp-uniform
+
+    const int64_t w = tile * 32 + lane;
+    const int64_t p0 = w * 32;
+
+    // ---- the lane's 64-base span of both streams --------------------------
+    const uint64_t f0 = __ldg(b.F + w), f1 = __ldg(b.F + w + 1);
+    const uint32_t d = __ldg(b.dirty + tile), dn = __ldg(b.dirty + tile + 1);
+    const bool d0 = (d >> lane) & 1u;
+    const bool d1 = lane < 31 ? (d >> (lane + 1)) & 1u : dn & 1u;
+    const uint64_t e0 = d0 ? b.E[w] : f0;
+    const uint64_t e1 = d1 ? b.E[w + 1] : f1;
+    // reverse complement of the span: base s of the span sits at base 63-s
+    const uint64_t r_lo = tb_revcomp64(e1), r_hi = tb_revcomp64(e0);
+
+    // ---- which read(s) do the lane's 32 window starts belong to? ----------
+    const int64_t *__restrict__ off = b.offsets;
+    int64_t r = 0, start = 0, end = 0;
+    uint32_t vmask = 0;
+    bool fast = false;
+    if (p0 < b.total_bases) {
+        r = b.tile_first_read[tile];
+        while (off[r + 1] <= p0) r++;
+        start = off[r];
+        end = off[r + 1];
+        fast = (p0 + 31 + k <= end) && ((uint64_t)(p0 - start) >= (uint64_t)b.skip[r]);
+        if (fast) {
+            vmask = 0xFFFFFFFFu;
+        } else {
+            int64_t rr = r, s = start, e = end;
+            uint32_t sk = b.skip[rr];
+            for (int j = 0; j < 32; j++) {
+                const int64_t pos = p0 + j;
+                if (pos >= b.total_bases) break;
+                while (e <= pos) {
+                    rr++;
+                    s = e;
+                    e = off[rr + 1];
+                    sk = b.skip[rr];
+                }
+                if (pos + k <= e && (uint64_t)(pos - s) >= (uint64_t)sk) vmask |= 1u << j;
+            }
+        }
+    }
+
+    // ---- probe every valid window: A first, B only where A missed (Q4) -----
+    uint32_t hit_a = 0, hit_b = 0;
+#pragma unroll
+    for (int g = 0; g < 32; g += U) {
+        const uint32_t gm = (vmask >> g) & ((U == 32) ? 0xFFFFFFFFu : ((1u << U) - 1u));
+        if (gm == 0) continue;
+        uint64_t key[U];
+        uint32_t h[U];
+        tb_bucket bk[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = g + u;
+            const uint64_t fwd = extract128(f0, f1, 2 * j) & kmask;
+            const uint64_t rc = extract128(r_lo, r_hi, 2 * (64 - j - k)) & kmask;
+            key[u] = fwd < rc ? fwd : rc;
+            h[u] = tb_hash32(key[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if ((gm >> u) & 1u) {
+                bk[u] = tb_load_bucket(A.table + __umulhi(h[u], A.n_buckets));
+            } else {
+                bk[u].s[0] = bk[u].s[1] = bk[u].s[2] = bk[u].s[3] = TB_EMPTY;
+            }
+        }
+        uint32_t ga = 0;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            bool hit = tb_bucket_has(bk[u], key[u]);
+            if (!hit && tb_bucket_full(bk[u]))
+                hit = tb_probe_overflow(A, key[u], __umulhi(h[u], A.n_buckets));
+            if (K == 0 || K == 32) {
+                if (key[u] == TB_EMPTY) hit = A.has_all_ones != 0;
+            }
+            ga |= (hit ? 1u : 0u) << u;
+        }
+        ga &= gm;
+        const uint32_t gmb = gm & ~ga;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if ((gmb >> u) & 1u) {
+                bk[u] = tb_load_bucket(B.table + __umulhi(h[u], B.n_buckets));
+            } else {
+                bk[u].s[0] = bk[u].s[1] = bk[u].s[2] = bk[u].s[3] = TB_EMPTY;
+            }
+        }
+        uint32_t gb = 0;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            bool hit = tb_bucket_has(bk[u], key[u]);
+            if (!hit && tb_bucket_full(bk[u]))
+                hit = tb_probe_overflow(B, key[u], __umulhi(h[u], B.n_buckets));
+            if (K == 0 || K == 32) {
+                if (key[u] == TB_EMPTY) hit = B.has_all_ones != 0;
+            }
+            gb |= (hit ? 1u : 0u) << u;
+        }
+        gb &= gmb;
+        hit_a |= ga << g;
+        hit_b |= gb << g;
+    }
+
+    // ---- attribute hits to reads -------------------------------------------
+    // common case: the whole warp sits inside one read -> one atomic per warp
+    const int64_t r0 = __shfl_sync(0xFFFFFFFFu, r, 0);
+    const bool uniform = __all_sync(0xFFFFFFFFu, fast && r == r0);
+    if (uniform) {
+        int ca = __reduce_add_sync(0xFFFFFFFFu, __popc(hit_a));
+        int cb = __reduce_add_sync(0xFFFFFFFFu, __popc(hit_b));
+        if (lane == 0) {
+            if (ca) atomicAdd(&b.count_a[r0], ca);
+            if (cb) atomicAdd(&b.count_b[r0], cb);
+        }
+    } else if (hit_a | hit_b) {
+        if (fast) {
+            if (hit_a) atomicAdd(&b.count_a[r], __popc(hit_a));
+            if (hit_b) atomicAdd(&b.count_b[r], __popc(hit_b));
+        } else {
+            int64_t rr = r, e = end;
+            uint32_t m = hit_a | hit_b;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const int64_t pos = p0 + j;
+                while (e <= pos) {
+                    rr++;
+                    e = off[rr + 1];
+                }
+                if ((hit_a >> j) & 1u)
+                    atomicAdd(&b.count_a[rr], 1);
+                else
+                    atomicAdd(&b.count_b[rr], 1);
+            }
+        }
+    }
+}
+
+// ============================================================================
+// k_fixup: the Q3-UB corner, literally.  For a read with a non-ACGT byte among
+// its first k bases the reference's reverse-complement scratch holds slots that
+// were never written; the contract is "they read as 0".  One thread
+// per flagged read replays windows [0, skip) with a sticky k-digit buffer,
+// exactly as c/kmers.c:287-294 does, and adds the hits to the read's counts.
+// ============================================================================
+__global__ void __launch_bounds__(128)
+k_fixup(tb_batch_view b, int k, tb_set_view A, tb_set_view B)
+{
+    const unsigned n = *b.ub_count;
+    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t r = b.ub_list[i];
+        const unsigned char *read = b.ascii + b.offsets[r];
+        const uint32_t skip = b.skip[r];
+        uint64_t rc = 0;  // sticky digits, slot s at bits 2s, zero-initialised
+        int ca = 0, cb = 0;
+        for (uint32_t win = 0; win < skip; win++) {
+            uint64_t fwd = 0;
+            for (int j = 0; j < k; j++) {
+                unsigned char c = read[win + j];
+                if (tb_base_valid(c)) {
+                    uint64_t code = tb_base_code(c);
+                    fwd |= code << (2 * j);
+                    const int s = k - 1 - j;
+                    rc = (rc & ~(3ull << (2 * s))) | ((3ull - code) << (2 * s));
+                }
+            }
+            const uint64_t key = (fwd < rc ? fwd : rc) & kmask;
+            if (tb_contains(A, key))
+                ca++;
+            else if (tb_contains(B, key))
+                cb++;
+        }
+        if (ca) atomicAdd(&b.count_a[r], ca);
+        if (cb) atomicAdd(&b.count_b[r], cb);
+    }
+}
+
+// ============================================================================
+// k_finalize: classify_by_kmers.py:104-115 in IEEE fp64 on device.
+// ============================================================================
+__global__ void __launch_bounds__(256)
+k_finalize(tb_batch_view b, double scale_a, double scale_b)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) *b.ub_count = 0;  // ready for the next batch on this slot
+    if (r >= b.n_reads) return;
+    const double a = __dmul_rn((double)b.count_a[r], scale_a);
+    const double c = __dmul_rn((double)b.count_b[r], scale_b);
+    if (b.score_a) b.score_a[r] = a;
+    if (b.score_b) b.score_b[r] = c;
+    if (b.bin) b.bin[r] = a > c ? 'A' : (c > a ? 'B' : 'U');
+}
+
+int g_unroll = 8;
+int g_tpb = 128;
+
+template <int K>
+cudaError_t launch_classify_k(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
+                              cudaStream_t stream)
+{
+    const int tpb = g_tpb;
+    const int warps = tpb / 32;
+    const unsigned blocks = (unsigned)((b.n_tiles + warps - 1) / warps);
+    switch (g_unroll) {
+    case 4: k_classify<K, 4><<<blocks, tpb, 0, stream>>>(b, k, A, B); break;
+    case 16: k_classify<K, 16><<<blocks, tpb, 0, stream>>>(b, k, A, B); break;
+    default: k_classify<K, 8><<<blocks, tpb, 0, stream>>>(b, k, A, B); break;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+void tb_classify_config(int unroll, int threads_per_block)
+{
+    if (unroll == 4 || unroll == 8 || unroll == 16) g_unroll = unroll;
+    if (threads_per_block == 32 || threads_per_block == 64 || threads_per_block == 128)
+        g_tpb = threads_per_block;
+}
+
+cudaError_t tb_launch_pack(const tb_batch_view &b, int k, cudaStream_t stream)
+{
+    if (b.n_tiles == 0) return cudaSuccess;
+    // one extra tile so that F[n_tiles*32] and dirty[n_tiles], which lane 31 of the
+    // last tile reads, are always (re)written; 256 threads per block = 8 tiles
+    const unsigned blocks = (unsigned)(((b.n_tiles + 1) * 32 + 255) / 256);
+    k_pack<<<blocks, 256, 0, stream>>>(b, k);
+    return cudaGetLastError();
+}
+
+cudaError_t tb_launch_index(const tb_batch_view &b, int k, cudaStream_t stream)
+{
+    if (b.n_reads == 0) return cudaSuccess;
+    k_index<<<(unsigned)((b.n_reads + 255) / 256), 256, 0, stream>>>(b, k);
+    return cudaGetLastError();
+}
+
+cudaError_t tb_launch_classify(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
+                               cudaStream_t stream)
+{
+    if (b.n_tiles == 0) return cudaSuccess;
+    switch (k) {
+    case 21: return launch_classify_k<21>(b, k, A, B, stream);
+    case 31: return launch_classify_k<31>(b, k, A, B, stream);
+    default: return launch_classify_k<0>(b, k, A, B, stream);
+    }
+}
+
+cudaError_t tb_launch_fixup(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
+                            cudaStream_t stream)
+{
+    if (b.n_reads == 0) return cudaSuccess;
+    k_fixup<<<64, 128, 0, stream>>>(b, k, A, B);
+    return cudaGetLastError();
+}
+
+cudaError_t tb_launch_finalize(const tb_batch_view &b, double scale_a, double scale_b,
+                               cudaStream_t stream)
+{
+    const int64_t n = b.n_reads > 0 ? b.n_reads : 1;
+    k_finalize<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(b, scale_a, scale_b);
+    return cudaGetLastError();
+}

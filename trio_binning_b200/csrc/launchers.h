@@ -1,0 +1,68 @@
+// launchers.h -- host-callable launch wrappers of the sm_100a kernels.
+// (internal; the public C ABI is include/trio_kmers_b200.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kmer_device.cuh"
+
+// ---- set build (set_build.cu) ---------------------------------------------
+// counters[0] += newly inserted distinct keys, counters[1] |= saw key 2^64-1,
+// counters[2] |= malformed line seen (only when check_newline)
+cudaError_t tb_launch_insert_text(const char *d_text, uint64_t n_lines, uint64_t text_bytes,
+                                  int stride, int k, int check_newline, tb_bucket *table,
+                                  uint32_t n_buckets, unsigned long long *d_counters,
+                                  cudaStream_t stream);
+cudaError_t tb_launch_insert_keys(const uint64_t *d_keys, uint64_t n, tb_bucket *table,
+                                  uint32_t n_buckets, unsigned long long *d_counters,
+                                  cudaStream_t stream);
+cudaError_t tb_launch_contains(tb_set_view set, const uint64_t *d_keys, uint64_t n,
+                               unsigned char *d_out, cudaStream_t stream);
+
+// ---- classify (classify.cu) -------------------------------------------------
+// Flat-stream batch layout in HBM (see DESIGN.md "Data layout"):
+//   ascii   : total_bases bytes, reads concatenated, no separators
+//   offsets : n_reads+1 int64 base offsets
+//   F       : 2-bit forward codes, base i at bits [2(i%32)] of word i/32 (non-ACGT -> 0)
+//   E       : same for the fill-forward stream; only words whose dirty bit is set are valid
+//   dirty   : one u32 per tile (1024 bases = 32 words), bit l = word l has a non-ACGT base
+//   tile_first_read : read that contains flat position 1024*t
+//   flags   : per read, bit 1 = a non-ACGT byte inside its first k bases (Q3-UB corner)
+//   skip    : per read, number of leading windows left to the fix-up kernel
+struct tb_batch_view {
+    const unsigned char *ascii;
+    const int64_t *offsets;
+    int64_t n_reads;
+    int64_t total_bases;
+    int64_t n_tiles;
+    uint64_t *F;
+    uint64_t *E;
+    uint32_t *dirty;
+    uint32_t *tile_first_read;
+    uint32_t *flags;
+    uint32_t *skip;
+    uint32_t *ub_list;
+    unsigned int *ub_count;  // device counter; zero before the batch, reset by finalize
+    int32_t *count_a;
+    int32_t *count_b;
+    double *score_a;
+    double *score_b;
+    char *bin;
+};
+
+cudaError_t tb_launch_pack(const tb_batch_view &b, int k, cudaStream_t stream);
+cudaError_t tb_launch_index(const tb_batch_view &b, int k, cudaStream_t stream);
+cudaError_t tb_launch_classify(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
+                               cudaStream_t stream);
+cudaError_t tb_launch_fixup(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
+                            cudaStream_t stream);
+cudaError_t tb_launch_finalize(const tb_batch_view &b, double scale_a, double scale_b,
+                               cudaStream_t stream);
+
+// classify kernel tuning knobs (read once from the environment by capi.cu)
+void tb_classify_config(int unroll, int threads_per_block);
+
+// ---- microbenchmark (gather_bench.cu) ----------------------------------------
+cudaError_t tb_launch_gather(const void *d_buf, uint64_t n_sectors, int loads_in_flight,
+                             int threads_per_block, int blocks, int steps, int variant,
+                             unsigned long long *d_sink, cudaStream_t stream);

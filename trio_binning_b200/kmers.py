@@ -1,0 +1,454 @@
+"""k-mer sets and per-read k-mer counting on a B200.
+
+Host-side mirror of the reference's ctypes boundary
+(reference src/trio_binning/kmers.py): same public names, argument meaning and
+error behaviour --
+
+    create_kmer_hash_set(path) -> HashSet          (kmers.py:104-122)
+    count_kmers_in_read(read, A, B) -> (int, int)  (kmers.py:125-154)
+    get_number_kmers_in_set(set) -> int            (kmers.py:157-159)
+    kmer_to_int(kmer) -> int                       (kmers.py:80-82)
+    reverse_complement(kmer) -> str                (kmers.py:89-93)
+
+-- plus what a GPU needs and the reference lacks: many reads per call
+(`count_kmers_in_reads`, `classify_reads`), a double-buffered asynchronous
+`Classifier`, device selection and explicit destruction.
+
+Everything is computed by the CUDA library ``kmers_c<EXT_SUFFIX>`` that sits
+next to this file (built from csrc/ for sm_100a).  There is no CPU fallback:
+if the library is missing and cannot be built, importing this module raises
+ImportError, exactly like the reference does when its C library is missing
+(kmers.py:36-37); if no GPU is usable, the calls raise RuntimeError.
+"""
+import ctypes as C
+import os
+import sys
+from importlib.machinery import EXTENSION_SUFFIXES
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+
+
+def _locate_library() -> str:
+    """Same search as the reference (kmers.py:30-34): ``kmers_c`` + any of the
+    interpreter's extension suffixes, next to this module; last match wins."""
+    found = ""
+    for suffix in EXTENSION_SUFFIXES:
+        candidate = os.path.join(_PKG_DIR, "kmers_c" + suffix)
+        if os.path.isfile(candidate):
+            found = candidate
+    return found
+
+
+_lib_path = _locate_library()
+if not _lib_path:
+    # Source checkout without a built library: try to build it in-tree with nvcc.
+    try:
+        from . import _build
+
+        _lib_path = _build.build()
+    except Exception as exc:  # noqa: BLE001
+        raise ImportError(
+            "Cannot load kmers_c library (the CUDA build for sm_100a is missing and "
+            f"could not be produced: {exc}). There is no CPU fallback."
+        ) from exc
+
+lib = C.cdll.LoadLibrary(_lib_path)
+
+
+class _HashSet(C.Structure):
+    """`hash_set` of include/trio_kmers_b200.h.  The first five fields are the
+    reference's struct (c/kmers.c:12-38, kmers.py:53-59); the rest is opaque."""
+
+    _fields_ = [
+        ("kmers", C.POINTER(C.c_uint64)),
+        ("full", C.POINTER(C.c_ubyte)),
+        ("hash_size", C.c_int),
+        ("k", C.c_ubyte),
+        ("num_kmers", C.c_int),
+        ("magic", C.c_uint32),
+        ("device", C.c_int),
+        ("d_table", C.c_void_p),
+        ("n_buckets", C.c_uint32),
+        ("has_all_ones", C.c_uint32),
+        ("n_distinct", C.c_uint64),
+        ("build_ms", C.c_double),
+    ]
+
+
+HashSet = C.POINTER(_HashSet)
+_I32P = C.POINTER(C.c_int32)
+
+# ---- legacy symbols (the four the reference binds, kmers.py:62-93) --------------
+lib.create_kmer_hash_set.argtypes = [C.c_char_p]
+lib.create_kmer_hash_set.restype = HashSet
+lib.count_kmers_in_read.argtypes = [C.c_char_p, HashSet, HashSet, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+lib.count_kmers_in_read.restype = None
+lib.kmer_to_int.argtypes = [C.c_char_p, C.c_ubyte]
+lib.kmer_to_int.restype = C.c_uint64
+lib.reverse_complement.argtypes = [C.c_char_p, C.c_char_p, C.c_ubyte]
+lib.reverse_complement.restype = None
+lib.hash_function.argtypes = [C.c_uint64]
+lib.hash_function.restype = C.c_uint
+lib.kmer_in_hash_set.argtypes = [C.c_char_p, C.c_char_p, HashSet]
+lib.kmer_in_hash_set.restype = C.c_char
+
+# ---- B200 API ------------------------------------------------------------------
+lib.tb_last_error.restype = C.c_char_p
+lib.tb_version.restype = C.c_char_p
+lib.tb_device_count.restype = C.c_int
+lib.tb_set_device.argtypes = [C.c_int]
+lib.tb_get_device.restype = C.c_int
+lib.tb_device_info.argtypes = [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int),
+                               C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+lib.tb_host_alloc.argtypes = [C.c_uint64]
+lib.tb_host_alloc.restype = C.c_void_p
+lib.tb_host_free.argtypes = [C.c_void_p]
+lib.tb_host_free.restype = None
+lib.tb_set_create_from_file.argtypes = [C.c_char_p, C.c_int]
+lib.tb_set_create_from_file.restype = HashSet
+lib.tb_set_create_from_keys.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+lib.tb_set_create_from_keys.restype = HashSet
+lib.tb_set_destroy.argtypes = [HashSet]
+lib.tb_set_destroy.restype = None
+lib.tb_set_contains_keys.argtypes = [HashSet, C.c_void_p, C.c_uint64, C.c_void_p]
+lib.tb_set_load_factor.argtypes = [C.c_double]
+lib.tb_scaling_factors.argtypes = [HashSet, HashSet, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+lib.tb_scaling_factors.restype = None
+lib.tb_classify_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, HashSet, HashSet,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.tb_classifier_create.argtypes = [HashSet, HashSet, C.c_int64, C.c_int64, C.c_int]
+lib.tb_classifier_create.restype = C.c_void_p
+lib.tb_classifier_destroy.argtypes = [C.c_void_p]
+lib.tb_classifier_destroy.restype = None
+lib.tb_classifier_submit.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.tb_classifier_wait.argtypes = [C.c_void_p, C.c_int]
+lib.tb_classifier_mark.argtypes = [C.c_void_p, C.c_int, C.c_int]
+lib.tb_classifier_elapsed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+lib.tb_classifier_rerun_resident.argtypes = [C.c_void_p, C.c_int, C.c_int,
+                                             C.POINTER(C.c_float), C.POINTER(C.c_float)]
+lib.tb_classifier_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                    C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+lib.tb_gather_bench.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.POINTER(C.c_double), C.POINTER(C.c_float)]
+
+
+def _error() -> str:
+    return (lib.tb_last_error() or b"unknown error").decode("utf-8", "replace")
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(_error())
+
+
+# =============================================================================
+# the reference's public functions
+# =============================================================================
+
+def kmer_to_int(kmer: str) -> int:
+    """Convert a k-mer to its integer form: first base in the two least
+    significant bits, A=0 C=1 G=2 T=3, anything else 0 (c/kmers.c:50-72)."""
+    raw = kmer.encode("utf-8")
+    return int(lib.kmer_to_int(raw, C.c_ubyte(len(kmer))))
+
+
+def reverse_complement(kmer: str) -> str:
+    """Reverse-complement a k-mer; non-ACGT positions come back as 'x' because the
+    native routine does not write them (c/kmers.c:78-91, kmers.py:91)."""
+    raw = kmer.encode("utf-8")
+    out = C.create_string_buffer(b"x" * len(kmer), len(kmer) + 1)
+    lib.reverse_complement(raw, out, len(kmer))
+    return out.raw[: len(kmer)].decode("utf-8")
+
+
+def create_kmer_hash_set(kmer_file_path: str) -> "HashSet":
+    """Read a list of k-mers (one per line) into a GPU-resident hash set.
+
+    Mirrors kmers.py:104-122: IOError if the path is not a file, a progress line
+    on stderr, then the native call (here: mmap + sm_100a parse/insert kernel).
+    """
+    if not os.path.isfile(kmer_file_path):
+        raise IOError(f"Specified file {kmer_file_path} does not exist or is not file.")
+    print(f"Reading k-mers in {kmer_file_path}...", file=sys.stderr)
+    handle = lib.create_kmer_hash_set(os.fsencode(kmer_file_path))
+    if not handle:
+        raise RuntimeError(f"create_kmer_hash_set({kmer_file_path}): {_error()}")
+    return handle
+
+
+def count_kmers_in_read(read: str, kmers_hap_a: "HashSet", kmers_hap_b: "HashSet") -> Tuple[int, int]:
+    """Count the k-mers of one read found in set A and, failing that, in set B
+    (kmers.py:125-154).  One read = one batch of one through the CUDA kernels;
+    use `count_kmers_in_reads` for throughput."""
+    count_a, count_b = C.c_int(), C.c_int()
+    lib.count_kmers_in_read(read.encode("utf-8"), kmers_hap_a, kmers_hap_b,
+                            C.byref(count_a), C.byref(count_b))
+    if count_a.value < 0:
+        raise RuntimeError(f"count_kmers_in_read: {_error()}")
+    return count_a.value, count_b.value
+
+
+def get_number_kmers_in_set(kmer_hash_set: "HashSet") -> int:
+    """Number of k-mers (= lines of the file) in a set (kmers.py:157-159)."""
+    return kmer_hash_set.contents.num_kmers
+
+
+# =============================================================================
+# B200 additions
+# =============================================================================
+
+def version() -> str:
+    return lib.tb_version().decode()
+
+
+def device_count() -> int:
+    return int(lib.tb_device_count())
+
+
+def set_device(device: int) -> None:
+    """Select the GPU used by subsequently created sets (one process per GPU)."""
+    _check(lib.tb_set_device(device))
+
+
+def device_info(device: int = 0) -> dict:
+    name = C.create_string_buffer(256)
+    sms, hbm, l2 = C.c_int(), C.c_uint64(), C.c_uint64()
+    _check(lib.tb_device_info(device, name, 256, C.byref(sms), C.byref(hbm), C.byref(l2)))
+    return {"name": name.value.decode(), "sm_count": sms.value, "hbm_bytes": hbm.value,
+            "l2_bytes": l2.value}
+
+
+def set_load_factor(load_factor: float) -> None:
+    _check(lib.tb_set_load_factor(load_factor))
+
+
+def create_kmer_hash_set_from_ints(keys, k: int, device: Optional[int] = None) -> "HashSet":
+    """Build a set from RAW integer encodings (`kmer_to_int` values); num_kmers = len(keys)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    dev = lib.tb_get_device() if device is None else device
+    handle = lib.tb_set_create_from_keys(keys.ctypes.data, len(keys), k, dev)
+    if not handle:
+        raise RuntimeError(f"create_kmer_hash_set_from_ints: {_error()}")
+    return handle
+
+
+def destroy_kmer_hash_set(kmer_hash_set: "HashSet") -> None:
+    """Free the device table (the reference never frees its sets)."""
+    lib.tb_set_destroy(kmer_hash_set)
+
+
+def set_contains_ints(kmer_hash_set: "HashSet", keys) -> np.ndarray:
+    """Membership of already-canonicalised lookup keys (testing aid)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    out = np.zeros(len(keys), dtype=np.uint8)
+    _check(lib.tb_set_contains_keys(kmer_hash_set, keys.ctypes.data, len(keys), out.ctypes.data))
+    return out.astype(bool)
+
+
+def scaling_factors(kmers_hap_a: "HashSet", kmers_hap_b: "HashSet") -> Tuple[float, float]:
+    sa, sb = C.c_double(), C.c_double()
+    lib.tb_scaling_factors(kmers_hap_a, kmers_hap_b, C.byref(sa), C.byref(sb))
+    return sa.value, sb.value
+
+
+def pack_reads(reads: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
+    """Concatenate reads into (uint8 bases, int64 offsets), the batch input format.
+
+    Each read is UTF-8 encoded and cut at its first NUL byte, which is what the
+    reference's `read.encode("utf-8")` + C `strlen` see (kmers.py:147, c/kmers.c:285).
+    """
+    try:
+        blob = "".join(reads).encode("ascii")
+        lengths = np.fromiter((len(r) for r in reads), dtype=np.int64, count=len(reads))
+        if b"\x00" in blob:
+            raise UnicodeError
+    except UnicodeError:
+        parts = [r.encode("utf-8").split(b"\x00", 1)[0] for r in reads]
+        blob = b"".join(parts)
+        lengths = np.fromiter((len(p) for p in parts), dtype=np.int64, count=len(parts))
+    offsets = np.zeros(len(reads) + 1, dtype=np.int64)
+    np.cumsum(lengths, out=offsets[1:])
+    bases = np.frombuffer(blob, dtype=np.uint8)
+    return bases, offsets
+
+
+def classify_packed(bases: np.ndarray, offsets: np.ndarray, kmers_hap_a: "HashSet",
+                    kmers_hap_b: "HashSet", want_scores: bool = True):
+    """One batch: returns (count_a, count_b, score_a, score_b, bins) as numpy arrays
+    (scores/bins None unless requested).  bins holds ord('A'|'B'|'U')."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    ca = np.zeros(n, dtype=np.int32)
+    cb = np.zeros(n, dtype=np.int32)
+    sa = np.zeros(n, dtype=np.float64) if want_scores else None
+    sb = np.zeros(n, dtype=np.float64) if want_scores else None
+    bins = np.zeros(n, dtype=np.uint8) if want_scores else None
+    if n:
+        _check(lib.tb_classify_batch(
+            bases.ctypes.data, offsets.ctypes.data, n, kmers_hap_a, kmers_hap_b,
+            ca.ctypes.data, cb.ctypes.data,
+            sa.ctypes.data if want_scores else None, sb.ctypes.data if want_scores else None,
+            bins.ctypes.data if want_scores else None))
+    return ca, cb, sa, sb, bins
+
+
+def count_kmers_in_reads(reads: Sequence[str], kmers_hap_a: "HashSet",
+                         kmers_hap_b: "HashSet") -> List[Tuple[int, int]]:
+    """Batched `count_kmers_in_read`: one kernel pipeline for all reads."""
+    bases, offsets = pack_reads(reads)
+    ca, cb, _, _, _ = classify_packed(bases, offsets, kmers_hap_a, kmers_hap_b, want_scores=False)
+    return list(zip(ca.tolist(), cb.tolist()))
+
+
+def classify_reads(reads: Sequence[str], kmers_hap_a: "HashSet", kmers_hap_b: "HashSet"):
+    """Counts, size-normalised scores and the A/B/U call per read, all from the
+    device (classify_by_kmers.py:104-115).  Returns a list of
+    (count_a, count_b, score_a, score_b, bin) with bin in 'A','B','U'."""
+    bases, offsets = pack_reads(reads)
+    ca, cb, sa, sb, bins = classify_packed(bases, offsets, kmers_hap_a, kmers_hap_b)
+    letters = bins.tobytes().decode("ascii")
+    return list(zip(ca.tolist(), cb.tolist(), sa.tolist(), sb.tolist(), letters))
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a numpy array (for asynchronous copies)."""
+
+    def __init__(self, n_items: int, dtype):
+        self.dtype = np.dtype(dtype)
+        self.nbytes = max(1, int(n_items) * self.dtype.itemsize)
+        self.ptr = lib.tb_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise RuntimeError(f"pinned allocation failed: {_error()}")
+        raw = (C.c_ubyte * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(raw, dtype=self.dtype, count=int(n_items))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib.tb_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class Classifier:
+    """Double-buffered asynchronous classifier (tb_classifier_* of the C ABI).
+
+    Each slot owns a CUDA stream, device buffers and pinned host staging/result
+    buffers.  `submit(slot, bases, offsets)` copies the batch into the slot's
+    pinned buffers and enqueues H2D + kernels + D2H; `result(slot)` waits and
+    returns views of the slot's pinned result arrays (valid until the slot is
+    submitted again)."""
+
+    def __init__(self, kmers_hap_a, kmers_hap_b, max_bases: int, max_reads: int, n_slots: int = 2):
+        self.max_bases, self.max_reads, self.n_slots = int(max_bases), int(max_reads), int(n_slots)
+        self._sets = (kmers_hap_a, kmers_hap_b)  # keep alive
+        self._h = lib.tb_classifier_create(kmers_hap_a, kmers_hap_b, self.max_bases, self.max_reads, n_slots)
+        if not self._h:
+            raise RuntimeError(f"Classifier: {_error()}")
+        self._slots = []
+        for _ in range(n_slots):
+            self._slots.append({
+                "bases": PinnedBuffer(self.max_bases, np.uint8),
+                "offsets": PinnedBuffer(self.max_reads + 1, np.int64),
+                "ca": PinnedBuffer(self.max_reads, np.int32),
+                "cb": PinnedBuffer(self.max_reads, np.int32),
+                "sa": PinnedBuffer(self.max_reads, np.float64),
+                "sb": PinnedBuffer(self.max_reads, np.float64),
+                "bins": PinnedBuffer(self.max_reads, np.uint8),
+                "n": 0,
+            })
+
+    def staging(self, slot: int):
+        """The slot's pinned (bases, offsets) arrays, to be filled in place."""
+        s = self._slots[slot]
+        return s["bases"].array, s["offsets"].array
+
+    def submit(self, slot: int, bases: Optional[np.ndarray], offsets: Optional[np.ndarray],
+               n_reads: Optional[int] = None, want_scores: bool = True) -> None:
+        """Enqueue a batch.  With bases/offsets given they are first copied into the
+        pinned staging arrays; with None the staging arrays are used as filled."""
+        s = self._slots[slot]
+        if offsets is not None:
+            n_reads = len(offsets) - 1
+            total = int(offsets[-1]) if n_reads else 0
+            if n_reads > self.max_reads or total > self.max_bases:
+                raise ValueError("batch exceeds classifier capacity")
+            s["offsets"].array[: n_reads + 1] = offsets
+            s["bases"].array[:total] = bases[:total]
+        s["n"] = int(n_reads)
+        s["scores"] = want_scores
+        _check(lib.tb_classifier_submit(
+            self._h, slot, s["bases"].ptr, s["offsets"].ptr, s["n"], s["ca"].ptr, s["cb"].ptr,
+            s["sa"].ptr if want_scores else None, s["sb"].ptr if want_scores else None,
+            s["bins"].ptr if want_scores else None))
+
+    def wait(self, slot: int) -> None:
+        _check(lib.tb_classifier_wait(self._h, slot))
+
+    def result(self, slot: int):
+        self.wait(slot)
+        s, n = self._slots[slot], self._slots[slot]["n"]
+        if s.get("scores", True):
+            return s["ca"].array[:n], s["cb"].array[:n], s["sa"].array[:n], s["sb"].array[:n], s["bins"].array[:n]
+        return s["ca"].array[:n], s["cb"].array[:n], None, None, None
+
+    def mark(self, slot: int, which: int) -> None:
+        """Record timing event `which` (0/1) at the current tail of the slot's stream."""
+        _check(lib.tb_classifier_mark(self._h, slot, which))
+
+    def elapsed_ms(self, slot_from: int, which_from: int, slot_to: int, which_to: int) -> float:
+        ms = C.c_float()
+        _check(lib.tb_classifier_elapsed(self._h, slot_from, which_from, slot_to, which_to, C.byref(ms)))
+        return ms.value
+
+    def rerun_resident(self, slot: int, iters: int) -> Tuple[float, float]:
+        """Re-run the device part of the slot's last batch `iters` times with no
+        copies; returns (total ms, ms spent in the classify kernel)."""
+        total, cls = C.c_float(), C.c_float()
+        _check(lib.tb_classifier_rerun_resident(self._h, slot, iters, C.byref(total), C.byref(cls)))
+        return total.value, cls.value
+
+    def stats(self, slot: int) -> dict:
+        w, p, f, launches = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(lib.tb_classifier_stats(self._h, slot, C.byref(w), C.byref(p), C.byref(f), C.byref(launches)))
+        return {"windows": w.value, "probes": p.value, "fixup_reads": f.value,
+                "kernel_launches": launches.value}
+
+    def close(self) -> None:
+        if self._h:
+            lib.tb_classifier_destroy(self._h)
+            self._h = None
+            for s in self._slots:
+                for key in ("bases", "offsets", "ca", "cb", "sa", "sb", "bins"):
+                    s[key].free()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def gather_bench(table_bytes: int, loads_in_flight: int = 8, threads_per_block: int = 256,
+                 blocks_per_sm: int = 8, steps: int = 64, variant: int = 0) -> Tuple[float, float]:
+    """Random-32-B-sector gather ceiling on this GPU: (sectors per second, ms)."""
+    rate, ms = C.c_double(), C.c_float()
+    _check(lib.tb_gather_bench(table_bytes, loads_in_flight, threads_per_block, blocks_per_sm,
+                               steps, variant, C.byref(rate), C.byref(ms)))
+    return rate.value, ms.value
