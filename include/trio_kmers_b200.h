@@ -154,6 +154,9 @@ int tb_classifier_elapsed(tb_classifier *c, int slot_from, int which_from, int s
  * for the HBM-resident figure and the roofline. */
 int tb_classifier_rerun_resident(tb_classifier *c, int slot, int iters,
                                  float *ms_total, float *ms_classify);
+/* The classifier's L2-resident pre-filter: log2 of its size in bits (0 = none, the
+ * direct kernel is used) and the device time spent building it. */
+int tb_classifier_filter_info(tb_classifier *c, int *log2_bits, float *build_ms);
 /* Counters of the last batch in a slot: windows, probes as the reference performs
  * them (W + (W - hits_A)), reads that took the Q3-UB fix-up path. */
 int tb_classifier_stats(tb_classifier *c, int slot, uint64_t *n_windows,

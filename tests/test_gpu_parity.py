@@ -389,3 +389,40 @@ def test_config2_full_size_properties(kmers, oracle, tmp_path_factory):
     owner = np.array(owner)
     assert (np.bincount(owner, weights=pa_, minlength=500) == ca[:500]).all()
     assert (np.bincount(owner, weights=pb_, minlength=500) == cb[:500]).all()
+
+
+# ---------------------------------------------------------------- pre-filter on / off
+@pytest.mark.parametrize("k", [21, 32, 9])
+def test_prefilter_does_not_change_results(kmers, oracle, k):
+    """The L2-resident bitmap in front of the exact tables may only skip work: direct
+    kernel (TB_FILTER_LOG2=0), a saturated 1-kbit bitmap (everything passes), a sparse one
+    and the automatic size all give the oracle's counts."""
+    from trio_binning_b200 import synth
+
+    ka, kb = synth.random_kmer_sets(30000, 20000, k, seed=77 + k)
+    bases, offsets, _ = synth.random_reads(400, 2500, k, ka, kb, seed=5, plant_every=150, invalid_rate=0.003)
+    bases = bases.copy()
+    bases[offsets[3]:offsets[3] + 5] = ord("N")          # exercise the fix-up path as well
+    A = kmers.create_kmer_hash_set_from_ints(ka, k)
+    B = kmers.create_kmer_hash_set_from_ints(kb, k)
+    oa, ob = oracle.set_from_ints(ka, k), oracle.set_from_ints(kb, k)
+    wa, wb = oracle.count_batch(bases, offsets, oa, ob)
+    seen = set()
+    old = os.environ.get("TB_FILTER_LOG2")
+    try:
+        for setting in ("0", "10", "20", "26", None):
+            if setting is None:
+                os.environ.pop("TB_FILTER_LOG2", None)
+            else:
+                os.environ["TB_FILTER_LOG2"] = setting
+            with kmers.Classifier(A, B, int(offsets[-1]), len(offsets) - 1, 1) as clf:
+                seen.add(clf.filter_info()["log2_bits"])
+                clf.submit(0, bases, offsets)
+                ca, cb, *_ = clf.result(0)
+                assert (ca == wa).all() and (cb == wb).all(), setting
+    finally:
+        if old is None:
+            os.environ.pop("TB_FILTER_LOG2", None)
+        else:
+            os.environ["TB_FILTER_LOG2"] = old
+    assert {0, 10, 20, 26} <= seen

@@ -9,14 +9,16 @@ based on the presence of k-mers.
 # (:99-117).  The per-read ctypes call of the reference's loop is replaced by
 # batches: reads are gathered until a batch holds --batch-bases bases, the batch
 # is counted and decided (A/B/U, fp64) on the GPU, and records/TSV lines are
-# written in input order.
+# written in input order.  Launched under torchrun, batches are dealt round-robin
+# to one process per GPU (sharding.py) and rank 0 writes everything in input order.
 
 import argparse
+import os
 import sys
 from os import path
 from typing import Tuple
 
-from . import kmers, seq
+from . import kmers, seq, sharding
 
 DEFAULT_BATCH_BASES = 256 << 20
 
@@ -80,52 +82,57 @@ def calculate_scaling_factors(haplotype_a_kmers, haplotype_b_kmers) -> Tuple[flo
     return 1.0 * biggest / num_a, 1.0 * biggest / num_b
 
 
-def _flush(batch, set_a, set_b, outfiles, out):
-    """Classify one batch on the GPU and emit records + TSV lines in input order."""
-    if not batch:
-        return
-    results = kmers.classify_reads([r.seq for r in batch], set_a, set_b)
-    file_a, file_b, file_u = outfiles
-    for read, (_, _, score_a, score_b, read_bin) in zip(batch, results):
-        if read_bin == "A":
-            read.print(file=file_a)
-        elif read_bin == "B":
-            read.print(file=file_b)
-        else:
-            read.print(file=file_u)
-        print("\t".join(map(str, [read.name, read_bin, score_a, score_b])), file=out)
+def _emit(read, result, files, out):
+    """One read's record into the file of its bin and its TSV line (reference :104-117)."""
+    _, _, score_a, score_b, read_bin = result
+    file_a, file_b, file_u = files
+    if read_bin == "A":
+        read.print(file=file_a)
+    elif read_bin == "B":
+        read.print(file=file_b)
+    else:
+        read.print(file=file_u)
+    print("\t".join(map(str, [read.name, read_bin, score_a, score_b])), file=out)
 
 
 def main(argv=None):
     """Main method of program"""
+    # Under torchrun (WORLD_SIZE > 1) every rank drives its own GPU; the sets are built
+    # while the arguments are parsed, so the device has to be chosen first.
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        kmers.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    comm = sharding.Communicator.from_env()
+
     args = parse_args(argv)
 
     reads = seq.open_fastx_read(args.reads)
 
-    # three locals, released in this order when main() returns, like the reference's
-    file_a, file_b, file_u = seq.open_outfiles(
-        args.haplotype_a_out_prefix,
-        args.haplotype_b_out_prefix,
-        args.unclassified_out_prefix,
-        # reference :90 -- rstrip strips a CHARACTER SET, kept as is (quirk Q8)
-        path.splitext(args.reads.rstrip(".gz"))[1],
-        not args.no_gzip_output,
-    )
+    file_a = file_b = file_u = None
+    if comm.rank == 0:
+        # three locals, released in this order when main() returns, like the reference's
+        file_a, file_b, file_u = seq.open_outfiles(
+            args.haplotype_a_out_prefix,
+            args.haplotype_b_out_prefix,
+            args.unclassified_out_prefix,
+            # reference :90 -- rstrip strips a CHARACTER SET, kept as is (quirk Q8)
+            path.splitext(args.reads.rstrip(".gz"))[1],
+            not args.no_gzip_output,
+        )
 
     # The device computes count * scaling in fp64 with the same factors
     # (tb_scaling_factors); this call is kept for API parity and as a cross-check.
     scaling_a, scaling_b = calculate_scaling_factors(args.haplotype_a_kmers, args.haplotype_b_kmers)
     assert (scaling_a, scaling_b) == kmers.scaling_factors(args.haplotype_a_kmers, args.haplotype_b_kmers)
 
-    batch, batch_bases = [], 0
-    for read in reads:
-        batch.append(read)
-        batch_bases += len(read.seq)
-        if batch_bases >= args.batch_bases:
-            _flush(batch, args.haplotype_a_kmers, args.haplotype_b_kmers,
-                   (file_a, file_b, file_u), sys.stdout)
-            batch, batch_bases = [], 0
-    _flush(batch, args.haplotype_a_kmers, args.haplotype_b_kmers, (file_a, file_b, file_u), sys.stdout)
+    set_a, set_b = args.haplotype_a_kmers, args.haplotype_b_kmers
+    sharding.run_sharded(
+        reads,
+        classify_fn=lambda seqs: kmers.classify_reads(seqs, set_a, set_b),
+        emit_fn=lambda read, result: _emit(read, result, (file_a, file_b, file_u), sys.stdout),
+        batch_bases=args.batch_bases,
+        comm=comm,
+    )
 
 
 if __name__ == "__main__":

@@ -69,9 +69,16 @@ int use_device(int device)
     if (device < 64 && !g_device_ready[device]) {
         // A random probe needs one 32-byte sector; do not let L2 fetch 64/128 B for it.
         int gran = env_int("TB_L2_FETCH_GRANULARITY", 32);
-        if (gran > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
+        if (gran > 0) {
+            cudaError_t ge = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
+            size_t got = 0;
+            cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+            if (getenv("TB_VERBOSE"))
+                fprintf(stderr, "[tb] cudaLimitMaxL2FetchGranularity: asked %d -> %s, now %zu\n", gran,
+                        cudaGetErrorString(ge), got);
+        }
         cudaGetLastError();
-        tb_classify_config(env_int("TB_UNROLL", 8), env_int("TB_TPB", 128));
+        tb_classify_config(env_int("TB_UNROLL", 4), env_int("TB_TPB", 128), env_int("TB_FILTER_UNROLL", 16));
         g_device_ready[device] = true;
     }
     return 0;
@@ -280,6 +287,11 @@ struct tb_classifier {
     double scale_a, scale_b;
     int64_t max_bases, max_reads;
     std::vector<Slot> slots;
+    // L2-resident pre-filter over the keys of A and B (nullptr = direct kernel)
+    uint32_t *d_filter = nullptr;
+    uint32_t filter_mask = 0;
+    int filter_log2 = 0;
+    float filter_build_ms = 0;
 };
 
 namespace {
@@ -335,10 +347,49 @@ int enqueue_kernels(tb_classifier *c, Slot &s, cudaEvent_t before_classify, cuda
     CK(tb_launch_pack(s.view, c->k, s.stream));
     CK(tb_launch_index(s.view, c->k, s.stream));
     if (before_classify) CK(cudaEventRecord(before_classify, s.stream));
-    CK(tb_launch_classify(s.view, c->k, A, B, s.stream));
+    if (c->d_filter)
+        CK(tb_launch_classify_filtered(s.view, c->k, A, B, c->d_filter, c->filter_mask, s.stream));
+    else
+        CK(tb_launch_classify(s.view, c->k, A, B, s.stream));
     if (after_classify) CK(cudaEventRecord(after_classify, s.stream));
     CK(tb_launch_fixup(s.view, c->k, A, B, s.stream));
     CK(tb_launch_finalize(s.view, c->scale_a, c->scale_b, s.stream));
+    return 0;
+}
+
+// Bitmap pre-filter over (A u B): 2^m bits, m chosen so that the bitmap holds >= 16
+// bits per distinct key but never more than 2^29 bits = 64 MB, the size up to which a
+// randomly read table stays L2-resident on B200 (profiles/gather_l2curve_r1.txt).
+// TB_FILTER_LOG2=0 disables it, another value forces m.
+int build_filter(tb_classifier *c)
+{
+    int m = env_int("TB_FILTER_LOG2", -1);
+    if (m == 0) return 0;
+    if (m < 0) {
+        const uint64_t n = c->A->n_distinct + c->B->n_distinct;
+        m = 16;
+        while (m < 29 && (1ull << m) < 16 * n) m++;
+    }
+    if (m < 10) m = 10;
+    if (m > 32) m = 32;
+    const uint64_t bits = 1ull << m;
+    CK(cudaMalloc((void **)&c->d_filter, bits / 8));
+    CK(cudaMemset(c->d_filter, 0, bits / 8));
+    c->filter_mask = (uint32_t)(bits - 1);
+    c->filter_log2 = m;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, 0));
+    CK(tb_launch_filter_build(c->A->d_table, (uint64_t)c->A->n_buckets * TB_SLOTS, c->d_filter,
+                              c->filter_mask, 0));
+    CK(tb_launch_filter_build(c->B->d_table, (uint64_t)c->B->n_buckets * TB_SLOTS, c->d_filter,
+                              c->filter_mask, 0));
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&c->filter_build_ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     return 0;
 }
 
@@ -544,6 +595,12 @@ tb_classifier *tb_classifier_create(const hash_set *A, const hash_set *B, int64_
     c->max_bases = max_bases;
     c->max_reads = max_reads;
     c->slots.resize((size_t)n_slots);
+    if (build_filter(c)) {
+        std::string keep = g_err;
+        tb_classifier_destroy(c);
+        g_err = keep;
+        return NULL;
+    }
     for (auto &s : c->slots) {
         if (alloc_slot(s, max_bases, max_reads)) {
             std::string keep = g_err;
@@ -563,6 +620,7 @@ void tb_classifier_destroy(tb_classifier *c)
         if (s.stream) cudaStreamSynchronize(s.stream);
         free_slot(s);
     }
+    if (c->d_filter) cudaFree(c->d_filter);
     delete c;
 }
 
@@ -712,6 +770,14 @@ int tb_classifier_stats(tb_classifier *c, int slot, uint64_t *n_windows, uint64_
         *n_fixup_reads = n;
     }
     if (n_kernel_launches) *n_kernel_launches = s.view.n_reads ? 5 : 0;
+    return 0;
+}
+
+int tb_classifier_filter_info(tb_classifier *c, int *log2_bits, float *build_ms)
+{
+    if (!c) return fail("null classifier");
+    if (log2_bits) *log2_bits = c->d_filter ? c->filter_log2 : 0;
+    if (build_ms) *build_ms = c->filter_build_ms;
     return 0;
 }
 

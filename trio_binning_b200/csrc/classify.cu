@@ -174,7 +174,7 @@ k_index(tb_batch_view b, int k)
 }
 
 // ============================================================================
-// k_classify
+// k_classify (direct) and k_classify_filtered (L2-resident pre-filter)
 // ============================================================================
 
 // bits [shift, shift+64) of the 128-bit value hi:lo  (0 <= shift < 128)
@@ -185,47 +185,60 @@ __device__ __forceinline__ uint64_t extract128(uint64_t lo, uint64_t hi, int shi
     return (lo >> shift) | (hi << (64 - shift));
 }
 
-template <int K, int U>
-__global__ void __launch_bounds__(128)
-k_classify(tb_batch_view b, int k_runtime, tb_set_view A, tb_set_view B)
+// What one lane knows about its 32 window-start positions.
+struct LaneCtx {
+    uint64_t f0, f1;      // forward stream, 64 bases starting at the lane's first position
+    uint64_t r_lo, r_hi;  // reverse complement of the same span of the E stream
+    int64_t p0;           // flat position of window 0
+    int64_t r, end;       // read containing p0 and its end offset
+    uint32_t vmask;       // bit j: window j lies inside one read and is not left to k_fixup
+    bool fast;            // all 32 windows valid and in read r
+};
+
+template <int K>
+__device__ __forceinline__ uint64_t window_key(const LaneCtx &c, int j, int k, uint64_t kmask)
 {
-    const int k = K ? K : k_runtime;
-    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
-    const int lane = threadIdx.x & 31;
-    const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (tile >= b.n_tiles) return;  // warp-uniform
+    const uint64_t fwd = extract128(c.f0, c.f1, 2 * j) & kmask;
+    // window j = bases [j, j+k) of the span = bases [64-j-k, 64-j) of its reverse complement
+    const uint64_t rc = extract128(c.r_lo, c.r_hi, 2 * (64 - j - k)) & kmask;
+    return fwd < rc ? fwd : rc;
+}
 
+__device__ __forceinline__ void lane_setup(const tb_batch_view &b, int64_t tile, int lane, int k,
+                                           LaneCtx &c)
+{
     const int64_t w = tile * 32 + lane;
-    const int64_t p0 = w * 32;
-
-    // ---- the lane's 64-base span of both streams --------------------------
-    const uint64_t f0 = __ldg(b.F + w), f1 = __ldg(b.F + w + 1);
+    c.p0 = w * 32;
+    c.f0 = __ldg(b.F + w);
+    c.f1 = __ldg(b.F + w + 1);
     const uint32_t d = __ldg(b.dirty + tile), dn = __ldg(b.dirty + tile + 1);
     const bool d0 = (d >> lane) & 1u;
     const bool d1 = lane < 31 ? (d >> (lane + 1)) & 1u : dn & 1u;
-    const uint64_t e0 = d0 ? b.E[w] : f0;
-    const uint64_t e1 = d1 ? b.E[w + 1] : f1;
+    const uint64_t e0 = d0 ? b.E[w] : c.f0;
+    const uint64_t e1 = d1 ? b.E[w + 1] : c.f1;
     // reverse complement of the span: base s of the span sits at base 63-s
-    const uint64_t r_lo = tb_revcomp64(e1), r_hi = tb_revcomp64(e0);
+    c.r_lo = tb_revcomp64(e1);
+    c.r_hi = tb_revcomp64(e0);
 
-    // ---- which read(s) do the lane's 32 window starts belong to? ----------
     const int64_t *__restrict__ off = b.offsets;
-    int64_t r = 0, start = 0, end = 0;
-    uint32_t vmask = 0;
-    bool fast = false;
-    if (p0 < b.total_bases) {
-        r = b.tile_first_read[tile];
-        while (off[r + 1] <= p0) r++;
-        start = off[r];
-        end = off[r + 1];
-        fast = (p0 + 31 + k <= end) && ((uint64_t)(p0 - start) >= (uint64_t)b.skip[r]);
-        if (fast) {
-            vmask = 0xFFFFFFFFu;
+    c.r = 0;
+    c.end = 0;
+    c.vmask = 0;
+    c.fast = false;
+    if (c.p0 < b.total_bases) {
+        int64_t r = b.tile_first_read[tile];
+        while (off[r + 1] <= c.p0) r++;
+        const int64_t start = off[r], end = off[r + 1];
+        c.r = r;
+        c.end = end;
+        c.fast = (c.p0 + 31 + k <= end) && ((uint64_t)(c.p0 - start) >= (uint64_t)b.skip[r]);
+        if (c.fast) {
+            c.vmask = 0xFFFFFFFFu;
         } else {
             int64_t rr = r, s = start, e = end;
             uint32_t sk = b.skip[rr];
             for (int j = 0; j < 32; j++) {
-                const int64_t pos = p0 + j;
+                const int64_t pos = c.p0 + j;
                 if (pos >= b.total_bases) break;
                 while (e <= pos) {
                     rr++;
@@ -233,95 +246,38 @@ k_classify(tb_batch_view b, int k_runtime, tb_set_view A, tb_set_view B)
                     e = off[rr + 1];
                     sk = b.skip[rr];
                 }
-                if (pos + k <= e && (uint64_t)(pos - s) >= (uint64_t)sk) vmask |= 1u << j;
+                if (pos + k <= e && (uint64_t)(pos - s) >= (uint64_t)sk) c.vmask |= 1u << j;
             }
         }
     }
+}
 
-    // ---- probe every valid window: A first, B only where A missed (Q4) -----
-    uint32_t hit_a = 0, hit_b = 0;
-#pragma unroll
-    for (int g = 0; g < 32; g += U) {
-        const uint32_t gm = (vmask >> g) & ((U == 32) ? 0xFFFFFFFFu : ((1u << U) - 1u));
-        if (gm == 0) continue;
-        uint64_t key[U];
-        uint32_t h[U];
-        tb_bucket bk[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int j = g + u;
-            const uint64_t fwd = extract128(f0, f1, 2 * j) & kmask;
-            const uint64_t rc = extract128(r_lo, r_hi, 2 * (64 - j - k)) & kmask;
-            key[u] = fwd < rc ? fwd : rc;
-            h[u] = tb_hash32(key[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if ((gm >> u) & 1u) {
-                bk[u] = tb_load_bucket(A.table + __umulhi(h[u], A.n_buckets));
-            } else {
-                bk[u].s[0] = bk[u].s[1] = bk[u].s[2] = bk[u].s[3] = TB_EMPTY;
-            }
-        }
-        uint32_t ga = 0;
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            bool hit = tb_bucket_has(bk[u], key[u]);
-            if (!hit && tb_bucket_full(bk[u]))
-                hit = tb_probe_overflow(A, key[u], __umulhi(h[u], A.n_buckets));
-            if (K == 0 || K == 32) {
-                if (key[u] == TB_EMPTY) hit = A.has_all_ones != 0;
-            }
-            ga |= (hit ? 1u : 0u) << u;
-        }
-        ga &= gm;
-        const uint32_t gmb = gm & ~ga;
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if ((gmb >> u) & 1u) {
-                bk[u] = tb_load_bucket(B.table + __umulhi(h[u], B.n_buckets));
-            } else {
-                bk[u].s[0] = bk[u].s[1] = bk[u].s[2] = bk[u].s[3] = TB_EMPTY;
-            }
-        }
-        uint32_t gb = 0;
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            bool hit = tb_bucket_has(bk[u], key[u]);
-            if (!hit && tb_bucket_full(bk[u]))
-                hit = tb_probe_overflow(B, key[u], __umulhi(h[u], B.n_buckets));
-            if (K == 0 || K == 32) {
-                if (key[u] == TB_EMPTY) hit = B.has_all_ones != 0;
-            }
-            gb |= (hit ? 1u : 0u) << u;
-        }
-        gb &= gmb;
-        hit_a |= ga << g;
-        hit_b |= gb << g;
-    }
-
-    // ---- attribute hits to reads -------------------------------------------
+// Add the lane's hits to the per-read counters.
+__device__ __forceinline__ void lane_attribute(const tb_batch_view &b, const LaneCtx &c, int lane,
+                                               uint32_t hit_a, uint32_t hit_b)
+{
     // common case: the whole warp sits inside one read -> one atomic per warp
-    const int64_t r0 = __shfl_sync(0xFFFFFFFFu, r, 0);
-    const bool uniform = __all_sync(0xFFFFFFFFu, fast && r == r0);
+    const int64_t r0 = __shfl_sync(0xFFFFFFFFu, c.r, 0);
+    const bool uniform = __all_sync(0xFFFFFFFFu, c.fast && c.r == r0);
     if (uniform) {
-        int ca = __reduce_add_sync(0xFFFFFFFFu, __popc(hit_a));
-        int cb = __reduce_add_sync(0xFFFFFFFFu, __popc(hit_b));
+        const int ca = __reduce_add_sync(0xFFFFFFFFu, __popc(hit_a));
+        const int cb = __reduce_add_sync(0xFFFFFFFFu, __popc(hit_b));
         if (lane == 0) {
             if (ca) atomicAdd(&b.count_a[r0], ca);
             if (cb) atomicAdd(&b.count_b[r0], cb);
         }
     } else if (hit_a | hit_b) {
-        if (fast) {
-            if (hit_a) atomicAdd(&b.count_a[r], __popc(hit_a));
-            if (hit_b) atomicAdd(&b.count_b[r], __popc(hit_b));
+        if (c.fast) {
+            if (hit_a) atomicAdd(&b.count_a[c.r], __popc(hit_a));
+            if (hit_b) atomicAdd(&b.count_b[c.r], __popc(hit_b));
         } else {
-            int64_t rr = r, e = end;
+            const int64_t *__restrict__ off = b.offsets;
+            int64_t rr = c.r, e = c.end;
             uint32_t m = hit_a | hit_b;
             while (m) {
                 const int j = __ffs(m) - 1;
                 m &= m - 1;
-                const int64_t pos = p0 + j;
+                const int64_t pos = c.p0 + j;
                 while (e <= pos) {
                     rr++;
                     e = off[rr + 1];
@@ -333,6 +289,166 @@ k_classify(tb_batch_view b, int k_runtime, tb_set_view A, tb_set_view B)
             }
         }
     }
+}
+
+// membership from an already loaded home bucket
+template <int K>
+__device__ __forceinline__ bool resolve(const tb_set_view &S, const tb_bucket &bk, uint64_t key,
+                                        uint32_t h)
+{
+    bool hit = tb_bucket_has(bk, key);
+    if (!hit && tb_bucket_full(bk)) hit = tb_probe_overflow(S, key, __umulhi(h, S.n_buckets));
+    if (K == 0 || K == 32) {
+        if (key == TB_EMPTY) hit = S.has_all_ones != 0;
+    }
+    return hit;
+}
+
+// ---- direct kernel: every window probes A, then B where A missed (Q4) -----------
+template <int K, int U>
+__global__ void __launch_bounds__(128)
+k_classify(tb_batch_view b, int k_runtime, tb_set_view A, tb_set_view B)
+{
+    const int k = K ? K : k_runtime;
+    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= b.n_tiles) return;  // warp-uniform
+    LaneCtx c;
+    lane_setup(b, tile, lane, k, c);
+
+    uint32_t hit_a = 0, hit_b = 0;
+#pragma unroll
+    for (int g = 0; g < 32; g += U) {
+        const uint32_t gm = (c.vmask >> g) & ((1u << U) - 1u);
+        if (gm == 0) continue;
+        uint64_t key[U];
+        uint32_t h[U];
+        tb_bucket bk[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            key[u] = window_key<K>(c, g + u, k, kmask);
+            h[u] = tb_hash32(key[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if ((gm >> u) & 1u)
+                bk[u] = tb_load_bucket(A.table + __umulhi(h[u], A.n_buckets));
+            else
+                bk[u].s[0] = bk[u].s[1] = bk[u].s[2] = bk[u].s[3] = TB_EMPTY;
+        }
+        uint32_t ga = 0;
+#pragma unroll
+        for (int u = 0; u < U; u++) ga |= (resolve<K>(A, bk[u], key[u], h[u]) ? 1u : 0u) << u;
+        ga &= gm;
+        const uint32_t gmb = gm & ~ga;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if ((gmb >> u) & 1u)
+                bk[u] = tb_load_bucket(B.table + __umulhi(h[u], B.n_buckets));
+            else
+                bk[u].s[0] = bk[u].s[1] = bk[u].s[2] = bk[u].s[3] = TB_EMPTY;
+        }
+        uint32_t gb = 0;
+#pragma unroll
+        for (int u = 0; u < U; u++) gb |= (resolve<K>(B, bk[u], key[u], h[u]) ? 1u : 0u) << u;
+        gb &= gmb;
+        hit_a |= ga << g;
+        hit_b |= gb << g;
+    }
+    lane_attribute(b, c, lane, hit_a, hit_b);
+}
+
+// ---- filtered kernel ---------------------------------------------------------------
+// Phase 1: every window tests ONE bit of a bitmap over (A u B) that is sized to stay
+// resident in L2 (<= 64 MB): a clear bit proves the k-mer is in neither set -- the
+// common case by far -- without touching HBM.  Phase 2: only the windows whose bit is
+// set (true members + false positives) probe the exact tables in HBM, A then B.
+// Exactness is untouched: the bitmap can only say "maybe".
+__device__ __forceinline__ uint32_t ld_filter(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+template <int K, int U>
+__global__ void __launch_bounds__(128)
+k_classify_filtered(tb_batch_view b, int k_runtime, tb_set_view A, tb_set_view B,
+                    const uint32_t *__restrict__ filter, uint32_t filter_mask)
+{
+    const int k = K ? K : k_runtime;
+    const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= b.n_tiles) return;  // warp-uniform
+    LaneCtx c;
+    lane_setup(b, tile, lane, k, c);
+
+    // ---- phase 1: one filter bit per window, U loads in flight --------------------
+    uint32_t pass = 0;
+    if (c.vmask) {
+#pragma unroll
+        for (int g = 0; g < 32; g += U) {
+            uint32_t h[U], wd[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint64_t key = window_key<K>(c, g + u, k, kmask);
+                h[u] = tb_hash32(key);
+                if (K == 0 || K == 32) {
+                    // the out-of-band key (2^64-1) is not in the bitmap: force a pass
+                    if (key == TB_EMPTY) pass |= 1u << (g + u);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) wd[u] = ld_filter(filter + ((h[u] & filter_mask) >> 5));
+#pragma unroll
+            for (int u = 0; u < U; u++) pass |= ((wd[u] >> (h[u] & 31u)) & 1u) << (g + u);
+        }
+        pass &= c.vmask;
+    }
+
+    // ---- phase 2: exact probes for the survivors, two windows per round -----------
+    uint32_t hit_a = 0, hit_b = 0;
+    uint32_t m = pass;
+    while (m) {
+        const int j0 = __ffs(m) - 1;
+        m &= m - 1;
+        const int j1 = m ? __ffs(m) - 1 : -1;
+        if (m) m &= m - 1;
+        const uint64_t key0 = window_key<0>(c, j0, k, kmask);
+        const uint64_t key1 = window_key<0>(c, j1 < 0 ? j0 : j1, k, kmask);
+        const uint32_t h0 = tb_hash32(key0), h1 = tb_hash32(key1);
+        // all four buckets in flight at once; a hit in A simply discards the B answer
+        const tb_bucket a0 = tb_load_bucket(A.table + __umulhi(h0, A.n_buckets));
+        const tb_bucket a1 = tb_load_bucket(A.table + __umulhi(h1, A.n_buckets));
+        const tb_bucket b0 = tb_load_bucket(B.table + __umulhi(h0, B.n_buckets));
+        const tb_bucket b1 = tb_load_bucket(B.table + __umulhi(h1, B.n_buckets));
+        const bool ia0 = resolve<K>(A, a0, key0, h0);
+        const bool ib0 = !ia0 && resolve<K>(B, b0, key0, h0);
+        hit_a |= (ia0 ? 1u : 0u) << j0;
+        hit_b |= (ib0 ? 1u : 0u) << j0;
+        if (j1 >= 0) {
+            const bool ia1 = resolve<K>(A, a1, key1, h1);
+            const bool ib1 = !ia1 && resolve<K>(B, b1, key1, h1);
+            hit_a |= (ia1 ? 1u : 0u) << j1;
+            hit_b |= (ib1 ? 1u : 0u) << j1;
+        }
+    }
+    lane_attribute(b, c, lane, hit_a, hit_b);
+}
+
+// ---- bitmap construction: one thread per table slot ---------------------------------
+__global__ void __launch_bounds__(256)
+k_filter_build(const unsigned long long *__restrict__ slots, uint64_t n_slots, uint32_t *filter,
+               uint32_t filter_mask)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    const unsigned long long key = slots[i];
+    if (key == TB_EMPTY) return;
+    const uint32_t h = tb_hash32(key);
+    atomicOr(&filter[(h & filter_mask) >> 5], 1u << (h & 31u));
 }
 
 // ============================================================================
@@ -391,8 +507,9 @@ k_finalize(tb_batch_view b, double scale_a, double scale_b)
     if (b.bin) b.bin[r] = a > c ? 'A' : (c > a ? 'B' : 'U');
 }
 
-int g_unroll = 8;
+int g_unroll = 4;
 int g_tpb = 128;
+int g_filter_unroll = 16;
 
 template <int K>
 cudaError_t launch_classify_k(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
@@ -409,10 +526,26 @@ cudaError_t launch_classify_k(const tb_batch_view &b, int k, tb_set_view A, tb_s
     return cudaGetLastError();
 }
 
+template <int K>
+cudaError_t launch_filtered_k(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
+                              const uint32_t *filter, uint32_t filter_mask, cudaStream_t stream)
+{
+    const int tpb = g_tpb;
+    const int warps = tpb / 32;
+    const unsigned blocks = (unsigned)((b.n_tiles + warps - 1) / warps);
+    switch (g_filter_unroll) {
+    case 8: k_classify_filtered<K, 8><<<blocks, tpb, 0, stream>>>(b, k, A, B, filter, filter_mask); break;
+    case 32: k_classify_filtered<K, 32><<<blocks, tpb, 0, stream>>>(b, k, A, B, filter, filter_mask); break;
+    default: k_classify_filtered<K, 16><<<blocks, tpb, 0, stream>>>(b, k, A, B, filter, filter_mask); break;
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace
 
-void tb_classify_config(int unroll, int threads_per_block)
+void tb_classify_config(int unroll, int threads_per_block, int filter_unroll)
 {
+    if (filter_unroll == 8 || filter_unroll == 16 || filter_unroll == 32) g_filter_unroll = filter_unroll;
     if (unroll == 4 || unroll == 8 || unroll == 16) g_unroll = unroll;
     if (threads_per_block == 32 || threads_per_block == 64 || threads_per_block == 128)
         g_tpb = threads_per_block;
@@ -444,6 +577,27 @@ cudaError_t tb_launch_classify(const tb_batch_view &b, int k, tb_set_view A, tb_
     case 31: return launch_classify_k<31>(b, k, A, B, stream);
     default: return launch_classify_k<0>(b, k, A, B, stream);
     }
+}
+
+cudaError_t tb_launch_classify_filtered(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
+                                        const uint32_t *filter, uint32_t filter_mask,
+                                        cudaStream_t stream)
+{
+    if (b.n_tiles == 0) return cudaSuccess;
+    switch (k) {
+    case 21: return launch_filtered_k<21>(b, k, A, B, filter, filter_mask, stream);
+    case 31: return launch_filtered_k<31>(b, k, A, B, filter, filter_mask, stream);
+    default: return launch_filtered_k<0>(b, k, A, B, filter, filter_mask, stream);
+    }
+}
+
+cudaError_t tb_launch_filter_build(const uint64_t *d_table, uint64_t n_slots, uint32_t *filter,
+                                   uint32_t filter_mask, cudaStream_t stream)
+{
+    if (n_slots == 0) return cudaSuccess;
+    k_filter_build<<<(unsigned)((n_slots + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const unsigned long long *>(d_table), n_slots, filter, filter_mask);
+    return cudaGetLastError();
 }
 
 cudaError_t tb_launch_fixup(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,

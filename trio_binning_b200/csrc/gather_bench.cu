@@ -8,6 +8,7 @@
 //   variant 0: one 256-bit load  (ld.global.nc.L1::no_allocate.v4.u64) -- what the probe uses
 //   variant 1: two 128-bit loads of the same sector
 //   variant 2: one 64-bit load per sector (touches the sector, moves 8 bytes to the SM)
+//   variant 3/4: all 2/4 sectors of one random aligned 64-B / 128-B block (rate = blocks/s)
 #include "launchers.h"
 
 namespace {
@@ -22,6 +23,30 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h)
     return h;
 }
 
+// 32-byte load of one sector with assorted cache qualifiers (variants >= 5)
+template <int VARIANT>
+__device__ __forceinline__ tb_bucket load_q(const tb_bucket *p, uint64_t policy)
+{
+    tb_bucket b;
+    if (VARIANT == 5)
+        asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.s[0]), "=l"(b.s[1]), "=l"(b.s[2]), "=l"(b.s[3]) : "l"(p));
+    else if (VARIANT == 6)
+        asm volatile("ld.global.cv.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.s[0]), "=l"(b.s[1]), "=l"(b.s[2]), "=l"(b.s[3]) : "l"(p));
+    else if (VARIANT == 7)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.s[0]), "=l"(b.s[1]), "=l"(b.s[2]), "=l"(b.s[3]) : "l"(p));
+    else if (VARIANT == 8)
+        asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.s[0]), "=l"(b.s[1]), "=l"(b.s[2]), "=l"(b.s[3]) : "l"(p));
+    else if (VARIANT == 9 || VARIANT == 10)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(b.s[0]), "=l"(b.s[1]), "=l"(b.s[2]), "=l"(b.s[3]) : "l"(p), "l"(policy));
+    else if (VARIANT == 11)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.s[0]), "=l"(b.s[1]), "=l"(b.s[2]), "=l"(b.s[3]) : "l"(p));
+    else if (VARIANT == 12)
+        asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b.s[0]), "=l"(b.s[1]), "=l"(b.s[2]), "=l"(b.s[3]) : "l"(p));
+    else
+        b = tb_load_bucket(p);
+    return b;
+}
+
 template <int MLP, int VARIANT>
 __global__ void k_gather(const tb_bucket *__restrict__ buf, uint64_t n_sectors, int steps,
                          unsigned long long *sink)
@@ -29,6 +54,11 @@ __global__ void k_gather(const tb_bucket *__restrict__ buf, uint64_t n_sectors, 
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long acc = 0;
     uint32_t state = mix32(tid * 2654435761u + 12345u);
+    uint64_t policy = 0;
+    if (VARIANT == 9)
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (VARIANT == 10)
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
     for (int s = 0; s < steps; s++) {
         uint64_t idx[MLP];
 #pragma unroll
@@ -40,10 +70,10 @@ __global__ void k_gather(const tb_bucket *__restrict__ buf, uint64_t n_sectors, 
             uint64_t h = ((uint64_t)h1 << 32) | h2;
             idx[u] = __umul64hi(h, n_sectors);
         }
-        if (VARIANT == 0) {
+        if (VARIANT == 0 || VARIANT >= 5) {
             tb_bucket v[MLP];
 #pragma unroll
-            for (int u = 0; u < MLP; u++) v[u] = tb_load_bucket(buf + idx[u]);
+            for (int u = 0; u < MLP; u++) v[u] = load_q<VARIANT>(buf + idx[u], policy);
 #pragma unroll
             for (int u = 0; u < MLP; u++) acc ^= v[u].s[0] ^ v[u].s[1] ^ v[u].s[2] ^ v[u].s[3];
         } else if (VARIANT == 1) {
@@ -58,6 +88,21 @@ __global__ void k_gather(const tb_bucket *__restrict__ buf, uint64_t n_sectors, 
             }
 #pragma unroll
             for (int u = 0; u < MLP; u++) acc ^= v[u][0].x ^ v[u][0].y ^ v[u][1].x ^ v[u][1].y;
+        } else if (VARIANT == 3 || VARIANT == 4) {
+            // SPAN adjacent sectors of one aligned 64-B (3) or 128-B (4) block per unit:
+            // does DRAM hand out the neighbours for free?
+            constexpr int SPAN = VARIANT == 3 ? 2 : 4;
+            tb_bucket v[MLP][SPAN];
+#pragma unroll
+            for (int u = 0; u < MLP; u++) {
+                const tb_bucket *p = buf + (idx[u] & ~(uint64_t)(SPAN - 1));
+#pragma unroll
+                for (int q = 0; q < SPAN; q++) v[u][q] = tb_load_bucket(p + q);
+            }
+#pragma unroll
+            for (int u = 0; u < MLP; u++)
+#pragma unroll
+                for (int q = 0; q < SPAN; q++) acc ^= v[u][q].s[0] ^ v[u][q].s[3];
         } else {
             unsigned long long v[MLP];
 #pragma unroll
@@ -81,7 +126,10 @@ cudaError_t launch_v(const tb_bucket *buf, uint64_t n, int mlp, int tpb, int blo
     case 2: k_gather<2, VARIANT><<<blocks, tpb, 0, st>>>(buf, n, steps, sink); break;
     case 4: k_gather<4, VARIANT><<<blocks, tpb, 0, st>>>(buf, n, steps, sink); break;
     case 8: k_gather<8, VARIANT><<<blocks, tpb, 0, st>>>(buf, n, steps, sink); break;
-    case 16: k_gather<16, VARIANT><<<blocks, tpb, 0, st>>>(buf, n, steps, sink); break;
+    case 16:
+        if (VARIANT == 3 || VARIANT == 4) return cudaErrorInvalidValue;  // register budget
+        k_gather<((VARIANT == 3 || VARIANT == 4) ? 8 : 16), VARIANT><<<blocks, tpb, 0, st>>>(buf, n, steps, sink);
+        break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -98,6 +146,16 @@ cudaError_t tb_launch_gather(const void *d_buf, uint64_t n_sectors, int loads_in
     case 0: return launch_v<0>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
     case 1: return launch_v<1>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
     case 2: return launch_v<2>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
+    case 3: return launch_v<3>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
+    case 4: return launch_v<4>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
+    case 5: return launch_v<5>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
+    case 6: return launch_v<6>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
+    case 7: return launch_v<7>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
+    case 8: return launch_v<8>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
+    case 9: return launch_v<9>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
+    case 10: return launch_v<10>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
+    case 11: return launch_v<11>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
+    case 12: return launch_v<12>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
     default: return cudaErrorInvalidValue;
     }
 }

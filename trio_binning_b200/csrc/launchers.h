@@ -54,13 +54,19 @@ cudaError_t tb_launch_pack(const tb_batch_view &b, int k, cudaStream_t stream);
 cudaError_t tb_launch_index(const tb_batch_view &b, int k, cudaStream_t stream);
 cudaError_t tb_launch_classify(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
                                cudaStream_t stream);
+// filtered variant: `filter` is a bitmap of filter_mask+1 bits over the keys of A and B
+cudaError_t tb_launch_classify_filtered(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
+                                        const uint32_t *filter, uint32_t filter_mask,
+                                        cudaStream_t stream);
+cudaError_t tb_launch_filter_build(const uint64_t *d_table, uint64_t n_slots, uint32_t *filter,
+                                   uint32_t filter_mask, cudaStream_t stream);
 cudaError_t tb_launch_fixup(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
                             cudaStream_t stream);
 cudaError_t tb_launch_finalize(const tb_batch_view &b, double scale_a, double scale_b,
                                cudaStream_t stream);
 
 // classify kernel tuning knobs (read once from the environment by capi.cu)
-void tb_classify_config(int unroll, int threads_per_block);
+void tb_classify_config(int unroll, int threads_per_block, int filter_unroll);
 
 // ---- microbenchmark (gather_bench.cu) ----------------------------------------
 cudaError_t tb_launch_gather(const void *d_buf, uint64_t n_sectors, int loads_in_flight,

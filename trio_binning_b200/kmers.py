@@ -130,6 +130,7 @@ lib.tb_classifier_mark.argtypes = [C.c_void_p, C.c_int, C.c_int]
 lib.tb_classifier_elapsed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
 lib.tb_classifier_rerun_resident.argtypes = [C.c_void_p, C.c_int, C.c_int,
                                              C.POINTER(C.c_float), C.POINTER(C.c_float)]
+lib.tb_classifier_filter_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
 lib.tb_classifier_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
 lib.tb_gather_bench.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -417,6 +418,12 @@ class Classifier:
         total, cls = C.c_float(), C.c_float()
         _check(lib.tb_classifier_rerun_resident(self._h, slot, iters, C.byref(total), C.byref(cls)))
         return total.value, cls.value
+
+    def filter_info(self) -> dict:
+        """log2(bits) of the L2-resident pre-filter (0 = direct kernel) and its build time."""
+        m, ms = C.c_int(), C.c_float()
+        _check(lib.tb_classifier_filter_info(self._h, C.byref(m), C.byref(ms)))
+        return {"log2_bits": m.value, "build_ms": ms.value}
 
     def stats(self, slot: int) -> dict:
         w, p, f, launches = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
