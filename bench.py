@@ -18,8 +18,8 @@ A "step" is one pass of the hot path over that batch.
   roofline: classify kernel only: (32 B x probes + 0.25 B x bases) / kernel time
            against the measured HBM copy peak, plus the measured random-32-B-sector
            gather ceiling of the same GPU.
-Tables (2 x 160 MB) exceed the 126 MB L2, and every step re-reads them at random, so
-no explicit L2 flush is needed between iterations (config.l2 says so).
+Inputs and tables exceed the 126 MB L2 (config.l2); value_l2_flushed is the same
+measurement with L2 overwritten between the timed steps.
 """
 import argparse
 import json
@@ -99,7 +99,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -260,7 +260,9 @@ def workload_config(args, wl):
                         f"(raw orientation, ~50% findable), per GPU",
             "reads_per_gpu": wl["n_reads"], "bases_per_gpu": int(wl["offsets"][-1]),
             "k": wl["k"], "set_a": wl["n_a"], "set_b": wl["n_b"],
-            "l2": "tables (2 x 160 MB at load 0.5) exceed the 126 MB L2; random probes, no flush needed",
+            "l2": "per step the kernels read 250 MB of fresh input (ASCII + packed) and probe 2 x 160 MB of "
+                  "tables at random, both larger than the 126 MB L2, so steps are timed back to back; "
+                  "value_l2_flushed repeats the measurement with a 512 MB buffer overwritten between steps",
             "parallelism": f"reads sharded over {args.gpus} GPU(s), sets replicated, no collective"}
 
 
@@ -323,7 +325,10 @@ def run_gpu_arm(args, rank, local_rank, world):
     res_ms, cls_ms = clf.rerun_resident(0, args.steps)
     dist.barrier()
     clocks = sampler.stop()
+    # same, with a 512 MB buffer overwritten between the timed steps (cold L2 every step)
+    flush_ms, flush_cls_ms = clf.rerun_resident(0, args.steps, flush_bytes=512 << 20)
     res_ms_max = dist.reduce(res_ms, "MAX")
+    flush_ms_max = dist.reduce(flush_ms, "MAX")
     total_all = dist.reduce(total, "SUM")
     probes_all = dist.reduce(probes, "SUM")
 
@@ -331,29 +336,69 @@ def run_gpu_arm(args, rank, local_rank, world):
     clf.submit(0, None, None, n_reads=n_reads)
     ca2, cb2, *_ = clf.result(0)
     assert (ca2 == ca).all() and (cb2 == cb).all(), "re-run changed the results"
+    finfo = clf.filter_info()
+    passes = clf.filter_passes(0)
 
     line = None
     if rank == 0:
         hbm_gbs, peak_src = measured_peaks()
         cls_ms_per = cls_ms / args.steps
-        algo_bytes = 32.0 * probes + 0.25 * total
-        achieved = algo_bytes / (cls_ms_per * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_classify<21,8>", "achieved": achieved, "peak": hbm_gbs,
-                    "unit": "GB/s", "frac": achieved / hbm_gbs, "peak_source": peak_src,
-                    "traffic": None,
-                    "algorithmic_bytes_per_launch": algo_bytes,
-                    "probes_per_launch": probes, "kernel_ms": cls_ms_per,
-                    "probes_per_s": probes / (cls_ms_per * 1e-3),
-                    "kernel_share_of_step": cls_ms / res_ms}
+        cls_s = cls_ms_per * 1e-3
+        ceil_dram = ceil_l2 = None
         if not args.no_gather:
-            # random-32-B-sector gather ceiling of this GPU (north_star's probe roofline)
-            best = 0.0
-            for mlp, tpb, bps in ((8, 256, 8), (16, 256, 4), (4, 512, 4), (8, 128, 16)):
-                rate, _ = kmers.gather_bench(4 << 30, mlp, tpb, bps, 48, 0)
-                best = max(best, rate)
-            roofline["random_sector_ceiling_sectors_per_s"] = best
-            roofline["random_sector_ceiling_gbs"] = best * 32 / 1e9
-            roofline["frac_of_random_sector_ceiling"] = (probes / (cls_ms_per * 1e-3)) / best
+            # random-32-B-sector request ceilings of THIS GPU, same run: a table far larger
+            # than L2 (HBM random-access bound) and one that stays L2-resident
+            ceil_dram = max(kmers.gather_bench(4 << 30, mlp, tpb, bps, 48, 0)[0]
+                            for mlp, tpb, bps in ((8, 256, 8), (16, 256, 4), (4, 512, 4)))
+            ceil_l2 = max(kmers.gather_bench(32 << 20, mlp, tpb, bps, 256, 0)[0]
+                          for mlp, tpb, bps in ((8, 256, 8), (16, 256, 4), (8, 128, 16)))
+        if finfo["log2_bits"]:
+            # filtered kernel: one L2 sector request per window (bitmap) + two HBM sector
+            # requests (A and B bucket) per window that passed the bitmap
+            table_probes = 2 * passes
+            sector_requests = windows + table_probes
+            algo_bytes = 32.0 * sector_requests + 0.25 * total
+            achieved = algo_bytes / cls_s / 1e9
+            roofline = {
+                "bound": "l2", "kernel": f"k_classify_filtered<{k},16>",
+                "note": "the bitmap pre-filter (2^%d bits, L2-resident, evict_last) answers %.1f%% of the windows "
+                        "without touching HBM; the kernel is bound by L2 sector requests (1 per SM per clock), "
+                        "not by HBM -- see hbm{} for the HBM side" % (finfo["log2_bits"], 100.0 * (1 - passes / max(1, windows))),
+                "achieved": achieved,
+                "peak": (ceil_l2 * 32 / 1e9) if ceil_l2 else None,
+                "unit": "GB/s", "frac": (achieved / (ceil_l2 * 32 / 1e9)) if ceil_l2 else None,
+                "peak_source": "measured in this run: tb_gather_bench, random 32-B sector requests on a 32 MB (L2-resident) table",
+                "traffic": None,
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "sector_requests_per_launch": sector_requests,
+                "windows_per_launch": windows, "filter_passes_per_launch": passes,
+                "kernel_ms": cls_ms_per, "kernel_share_of_step": cls_ms / res_ms,
+                "reference_probes_per_launch": probes, "reference_probes_per_s": probes / cls_s,
+                "hbm": {"algorithmic_bytes_per_launch": 32.0 * table_probes + 0.25 * total,
+                        "achieved": (32.0 * table_probes + 0.25 * total) / cls_s / 1e9,
+                        "peak": hbm_gbs, "unit": "GB/s", "peak_source": peak_src,
+                        "frac": (32.0 * table_probes + 0.25 * total) / cls_s / 1e9 / hbm_gbs,
+                        "table_probes_per_s": table_probes / cls_s,
+                        "random_sector_ceiling_per_s": ceil_dram,
+                        "frac_of_random_sector_ceiling": (table_probes / cls_s / ceil_dram) if ceil_dram else None},
+            }
+        else:
+            algo_bytes = 32.0 * probes + 0.25 * total
+            achieved = algo_bytes / cls_s / 1e9
+            roofline = {"bound": "hbm", "kernel": f"k_classify<{k},4>", "achieved": achieved, "peak": hbm_gbs,
+                        "unit": "GB/s", "frac": achieved / hbm_gbs, "peak_source": peak_src, "traffic": None,
+                        "algorithmic_bytes_per_launch": algo_bytes, "probes_per_launch": probes,
+                        "kernel_ms": cls_ms_per, "probes_per_s": probes / cls_s,
+                        "kernel_share_of_step": cls_ms / res_ms,
+                        "random_sector_ceiling_per_s": ceil_dram,
+                        "frac_of_random_sector_ceiling": (probes / cls_s / ceil_dram) if ceil_dram else None}
+        traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(traffic_file):
+            with open(traffic_file) as f:
+                t = json.load(f).get(roofline["kernel"].split("<")[0])
+            if t:
+                roofline["traffic"] = t["dram_bytes_per_launch"]
+                roofline["traffic_source"] = t["source"]
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             kind = cpu_reference_setup(wl)
@@ -380,6 +425,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                     "ms_per_step": e2e_ms / args.steps,
                     "api": "tb_classifier_submit/wait (C ABI), pinned host buffers, 2 slots in flight"},
             "gpu_launches": 5 * args.steps,
+            "value_l2_flushed": total_all / (flush_ms_max / args.steps * 1e-3),
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
@@ -397,7 +443,7 @@ def run_gpu_arm(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))

@@ -154,6 +154,13 @@ int tb_classifier_elapsed(tb_classifier *c, int slot_from, int which_from, int s
  * for the HBM-resident figure and the roofline. */
 int tb_classifier_rerun_resident(tb_classifier *c, int slot, int iters,
                                  float *ms_total, float *ms_classify);
+/* Same, with `flush_bytes` > 0 overwriting a scratch buffer of that size between the
+ * timed steps (outside the timed intervals) so that no step starts with a warm L2. */
+int tb_classifier_rerun_resident_flush(tb_classifier *c, int slot, int iters, uint64_t flush_bytes,
+                                       float *ms_total, float *ms_classify);
+/* Number of windows of the slot's last batch whose pre-filter bit was set (they are the
+ * only ones that probed the tables in HBM); 0 when the direct kernel is in use. */
+int tb_classifier_filter_passes(tb_classifier *c, int slot, uint64_t *n_pass);
 /* The classifier's L2-resident pre-filter: log2 of its size in bits (0 = none, the
  * direct kernel is used) and the device time spent building it. */
 int tb_classifier_filter_info(tb_classifier *c, int *log2_bits, float *build_ms);

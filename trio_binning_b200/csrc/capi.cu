@@ -77,8 +77,20 @@ int use_device(int device)
                 fprintf(stderr, "[tb] cudaLimitMaxL2FetchGranularity: asked %d -> %s, now %zu\n", gran,
                         cudaGetErrorString(ge), got);
         }
+        // room for evict_last lines (the bitmap); harmless if the hint works without it
+        int persist_mb = env_int("TB_L2_PERSIST_MB", 0);  // measured: a carve-out does not help
+        if (persist_mb != 0) {
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+                size_t want = persist_mb > 0 ? (size_t)persist_mb << 20 : (size_t)prop.persistingL2CacheMaxSize;
+                cudaError_t pe = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+                if (getenv("TB_VERBOSE"))
+                    fprintf(stderr, "[tb] cudaLimitPersistingL2CacheSize %zu -> %s\n", want, cudaGetErrorString(pe));
+            }
+        }
         cudaGetLastError();
-        tb_classify_config(env_int("TB_UNROLL", 4), env_int("TB_TPB", 128), env_int("TB_FILTER_UNROLL", 16));
+        tb_classify_config(env_int("TB_UNROLL", 4), env_int("TB_TPB", 128), env_int("TB_FILTER_UNROLL", 16),
+                            env_int("TB_FILTER_MODE", 2));
         g_device_ready[device] = true;
     }
     return 0;
@@ -268,6 +280,7 @@ struct Slot {
     uint32_t *d_dirty = nullptr, *d_tile_first = nullptr, *d_flags = nullptr, *d_skip = nullptr,
              *d_ub_list = nullptr;
     unsigned int *d_ub_count = nullptr;
+    unsigned long long *d_n_pass = nullptr;
     int32_t *d_ca = nullptr, *d_cb = nullptr;
     double *d_sa = nullptr, *d_sb = nullptr;
     char *d_bin = nullptr;
@@ -299,7 +312,7 @@ namespace {
 void free_slot(Slot &s)
 {
     void *ptrs[] = { s.d_ascii, s.d_offsets, s.d_F, s.d_E, s.d_dirty, s.d_tile_first, s.d_flags,
-                     s.d_skip, s.d_ub_list, s.d_ub_count, s.d_ca, s.d_cb, s.d_sa, s.d_sb, s.d_bin };
+                     s.d_skip, s.d_ub_list, s.d_ub_count, s.d_n_pass, s.d_ca, s.d_cb, s.d_sa, s.d_sb, s.d_bin };
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; i++) {
@@ -329,6 +342,8 @@ int alloc_slot(Slot &s, int64_t max_bases, int64_t max_reads)
     CK(cudaMalloc((void **)&s.d_skip, (size_t)(max_reads + 1) * 4));
     CK(cudaMalloc((void **)&s.d_ub_list, (size_t)(max_reads + 1) * 4));
     CK(cudaMalloc((void **)&s.d_ub_count, 2 * sizeof(unsigned int)));
+    CK(cudaMalloc((void **)&s.d_n_pass, sizeof(unsigned long long)));
+    CK(cudaMemset(s.d_n_pass, 0, sizeof(unsigned long long)));
     CK(cudaMalloc((void **)&s.d_ca, (size_t)(max_reads + 1) * 4));
     CK(cudaMalloc((void **)&s.d_cb, (size_t)(max_reads + 1) * 4));
     CK(cudaMalloc((void **)&s.d_sa, (size_t)(max_reads + 1) * 8));
@@ -366,9 +381,13 @@ int build_filter(tb_classifier *c)
     int m = env_int("TB_FILTER_LOG2", -1);
     if (m == 0) return 0;
     if (m < 0) {
+        // >= 16 bits per key up to 2^29 bits (64 MB: what stays L2-resident next to the
+        // table traffic); very large sets do better with 2^30 although it spills
+        // (profiles/r1_kernel_variants_filtered.txt).
         const uint64_t n = c->A->n_distinct + c->B->n_distinct;
         m = 16;
         while (m < 29 && (1ull << m) < 16 * n) m++;
+        if (n >= (1ull << 27)) m = 30;
     }
     if (m < 10) m = 10;
     if (m > 32) m = 32;
@@ -662,6 +681,7 @@ int tb_classifier_submit(tb_classifier *c, int slot, const char *bases, const in
     v.skip = s.d_skip;
     v.ub_list = s.d_ub_list;
     v.ub_count = s.d_ub_count;
+    v.n_pass = s.d_n_pass;
     v.count_a = s.d_ca;
     v.count_b = s.d_cb;
     v.score_a = score_A ? s.d_sa : nullptr;
@@ -719,30 +739,57 @@ int tb_classifier_elapsed(tb_classifier *c, int slot_from, int which_from, int s
 int tb_classifier_rerun_resident(tb_classifier *c, int slot, int iters, float *ms_total,
                                  float *ms_classify)
 {
+    return tb_classifier_rerun_resident_flush(c, slot, iters, 0, ms_total, ms_classify);
+}
+
+int tb_classifier_rerun_resident_flush(tb_classifier *c, int slot, int iters, uint64_t flush_bytes,
+                                       float *ms_total, float *ms_classify)
+{
     if (!c) return fail("null classifier");
     if (slot < 0 || slot >= (int)c->slots.size()) return fail("slot %d out of range", slot);
     if (iters < 1 || iters > 4096) return fail("iters must be 1..4096");
     CK(cudaSetDevice(c->device));
     Slot &s = c->slots[(size_t)slot];
     if (!s.has_batch || s.view.n_reads == 0) return fail("no batch resident in slot %d", slot);
-    std::vector<cudaEvent_t> ev((size_t)iters * 2);
+    void *scratch = nullptr;
+    if (flush_bytes) CK(cudaMalloc(&scratch, flush_bytes));
+    // four events per iteration: step begin/end and classify begin/end
+    std::vector<cudaEvent_t> ev((size_t)iters * 4);
     for (auto &e : ev) CK(cudaEventCreate(&e));
     CK(cudaStreamSynchronize(s.stream));
-    CK(cudaEventRecord(s.ev[0], s.stream));
-    for (int i = 0; i < iters; i++)
-        if (enqueue_kernels(c, s, ev[(size_t)2 * i], ev[(size_t)2 * i + 1])) return -1;
-    CK(cudaEventRecord(s.ev[1], s.stream));
+    for (int i = 0; i < iters; i++) {
+        // between timed steps: overwrite a buffer larger than L2 so nothing survives in cache
+        if (scratch) CK(cudaMemsetAsync(scratch, i & 0xFF, flush_bytes, s.stream));
+        CK(cudaEventRecord(ev[(size_t)4 * i], s.stream));
+        if (enqueue_kernels(c, s, ev[(size_t)4 * i + 1], ev[(size_t)4 * i + 2])) return -1;
+        CK(cudaEventRecord(ev[(size_t)4 * i + 3], s.stream));
+    }
     CK(cudaStreamSynchronize(s.stream));
     float total = 0, cls = 0;
-    CK(cudaEventElapsedTime(&total, s.ev[0], s.ev[1]));
     for (int i = 0; i < iters; i++) {
         float t = 0;
-        CK(cudaEventElapsedTime(&t, ev[(size_t)2 * i], ev[(size_t)2 * i + 1]));
+        CK(cudaEventElapsedTime(&t, ev[(size_t)4 * i], ev[(size_t)4 * i + 3]));
+        total += t;
+        CK(cudaEventElapsedTime(&t, ev[(size_t)4 * i + 1], ev[(size_t)4 * i + 2]));
         cls += t;
     }
     for (auto &e : ev) cudaEventDestroy(e);
+    if (scratch) cudaFree(scratch);
     if (ms_total) *ms_total = total;
     if (ms_classify) *ms_classify = cls;
+    return 0;
+}
+
+int tb_classifier_filter_passes(tb_classifier *c, int slot, uint64_t *n_pass)
+{
+    if (!c) return fail("null classifier");
+    if (slot < 0 || slot >= (int)c->slots.size()) return fail("slot %d out of range", slot);
+    CK(cudaSetDevice(c->device));
+    Slot &s = c->slots[(size_t)slot];
+    CK(cudaStreamSynchronize(s.stream));
+    unsigned long long v = 0;
+    CK(cudaMemcpy(&v, s.d_n_pass, sizeof v, cudaMemcpyDeviceToHost));
+    if (n_pass) *n_pass = c->d_filter ? v : 0;
     return 0;
 }
 

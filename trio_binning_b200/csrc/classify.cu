@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(256)
 k_index(tb_batch_view b, int k)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) *b.n_pass = 0;
     if (r >= b.n_reads) return;
     const int64_t start = b.offsets[r], end = b.offsets[r + 1];
     for (int64_t t = (start + 1023) >> 10; (t << 10) < end; t++)
@@ -365,18 +366,30 @@ k_classify(tb_batch_view b, int k_runtime, tb_set_view A, tb_set_view B)
 // common case by far -- without touching HBM.  Phase 2: only the windows whose bit is
 // set (true members + false positives) probe the exact tables in HBM, A then B.
 // Exactness is untouched: the bitmap can only say "maybe".
-__device__ __forceinline__ uint32_t ld_filter(const uint32_t *p)
+// The bitmap must STAY in L2 while table sectors stream through it.  ncu shows that
+// L1::no_allocate loads are looked up as evict_first in L2 (lts__t_sectors_*_evict_first),
+// which made bitmap and table lines compete as equals; the bitmap is therefore read with
+// an explicit evict_last policy (mode 2), plain (evict_normal, mode 1) or as before (0).
+__device__ __forceinline__ uint32_t ld_filter(const uint32_t *p, int mode, uint64_t policy)
 {
     uint32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    if (mode == 2)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+    else if (mode == 1)
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
 
 template <int K, int U>
 __global__ void __launch_bounds__(128)
 k_classify_filtered(tb_batch_view b, int k_runtime, tb_set_view A, tb_set_view B,
-                    const uint32_t *__restrict__ filter, uint32_t filter_mask)
+                    const uint32_t *__restrict__ filter, uint32_t filter_mask, int filter_mode)
 {
+    uint64_t keep_policy = 0;
+    if (filter_mode == 2)
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
     const int k = K ? K : k_runtime;
     const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
     const int lane = threadIdx.x & 31;
@@ -401,11 +414,15 @@ k_classify_filtered(tb_batch_view b, int k_runtime, tb_set_view A, tb_set_view B
                 }
             }
 #pragma unroll
-            for (int u = 0; u < U; u++) wd[u] = ld_filter(filter + ((h[u] & filter_mask) >> 5));
+            for (int u = 0; u < U; u++) wd[u] = ld_filter(filter + ((h[u] & filter_mask) >> 5), filter_mode, keep_policy);
 #pragma unroll
             for (int u = 0; u < U; u++) pass |= ((wd[u] >> (h[u] & 31u)) & 1u) << (g + u);
         }
         pass &= c.vmask;
+    }
+    {
+        const unsigned np = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(pass));
+        if (lane == 0 && np) atomicAdd(b.n_pass, (unsigned long long)np);
     }
 
     // ---- phase 2: exact probes for the survivors, two windows per round -----------
@@ -510,6 +527,7 @@ k_finalize(tb_batch_view b, double scale_a, double scale_b)
 int g_unroll = 4;
 int g_tpb = 128;
 int g_filter_unroll = 16;
+int g_filter_mode = 2;
 
 template <int K>
 cudaError_t launch_classify_k(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
@@ -534,17 +552,18 @@ cudaError_t launch_filtered_k(const tb_batch_view &b, int k, tb_set_view A, tb_s
     const int warps = tpb / 32;
     const unsigned blocks = (unsigned)((b.n_tiles + warps - 1) / warps);
     switch (g_filter_unroll) {
-    case 8: k_classify_filtered<K, 8><<<blocks, tpb, 0, stream>>>(b, k, A, B, filter, filter_mask); break;
-    case 32: k_classify_filtered<K, 32><<<blocks, tpb, 0, stream>>>(b, k, A, B, filter, filter_mask); break;
-    default: k_classify_filtered<K, 16><<<blocks, tpb, 0, stream>>>(b, k, A, B, filter, filter_mask); break;
+    case 8: k_classify_filtered<K, 8><<<blocks, tpb, 0, stream>>>(b, k, A, B, filter, filter_mask, g_filter_mode); break;
+    case 32: k_classify_filtered<K, 32><<<blocks, tpb, 0, stream>>>(b, k, A, B, filter, filter_mask, g_filter_mode); break;
+    default: k_classify_filtered<K, 16><<<blocks, tpb, 0, stream>>>(b, k, A, B, filter, filter_mask, g_filter_mode); break;
     }
     return cudaGetLastError();
 }
 
 }  // namespace
 
-void tb_classify_config(int unroll, int threads_per_block, int filter_unroll)
+void tb_classify_config(int unroll, int threads_per_block, int filter_unroll, int filter_mode)
 {
+    if (filter_mode >= 0 && filter_mode <= 2) g_filter_mode = filter_mode;
     if (filter_unroll == 8 || filter_unroll == 16 || filter_unroll == 32) g_filter_unroll = filter_unroll;
     if (unroll == 4 || unroll == 8 || unroll == 16) g_unroll = unroll;
     if (threads_per_block == 32 || threads_per_block == 64 || threads_per_block == 128)

@@ -47,11 +47,14 @@ __device__ __forceinline__ uint32_t tb_bucket_of(uint64_t key, uint32_t n_bucket
 }
 
 // One 256-bit read-only load of a bucket.  L1::no_allocate: a probed sector is
-// never reused by this SM, keep L1 for the read stream.
+// never reused by this SM, keep L1 for the read stream.  L2::64B: by default an L2
+// miss on B200 fetches the whole 128-B line from HBM (measured 125 B of DRAM traffic
+// per random 32-B request, profiles/r1_gather_cache_qualifiers.txt); the 64-B
+// granularity is the smallest the ISA offers and halves that traffic.
 __device__ __forceinline__ tb_bucket tb_load_bucket(const tb_bucket *p)
 {
     tb_bucket b;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(b.s[0]), "=l"(b.s[1]), "=l"(b.s[2]), "=l"(b.s[3])
                  : "l"(p));
     return b;

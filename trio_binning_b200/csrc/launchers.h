@@ -43,6 +43,7 @@ struct tb_batch_view {
     uint32_t *skip;
     uint32_t *ub_list;
     unsigned int *ub_count;  // device counter; zero before the batch, reset by finalize
+    unsigned long long *n_pass;  // windows that passed the pre-filter (reset by k_index)
     int32_t *count_a;
     int32_t *count_b;
     double *score_a;
@@ -66,7 +67,7 @@ cudaError_t tb_launch_finalize(const tb_batch_view &b, double scale_a, double sc
                                cudaStream_t stream);
 
 // classify kernel tuning knobs (read once from the environment by capi.cu)
-void tb_classify_config(int unroll, int threads_per_block, int filter_unroll);
+void tb_classify_config(int unroll, int threads_per_block, int filter_unroll, int filter_mode);
 
 // ---- microbenchmark (gather_bench.cu) ----------------------------------------
 cudaError_t tb_launch_gather(const void *d_buf, uint64_t n_sectors, int loads_in_flight,

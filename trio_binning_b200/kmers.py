@@ -130,6 +130,9 @@ lib.tb_classifier_mark.argtypes = [C.c_void_p, C.c_int, C.c_int]
 lib.tb_classifier_elapsed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
 lib.tb_classifier_rerun_resident.argtypes = [C.c_void_p, C.c_int, C.c_int,
                                              C.POINTER(C.c_float), C.POINTER(C.c_float)]
+lib.tb_classifier_rerun_resident_flush.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64,
+                                                   C.POINTER(C.c_float), C.POINTER(C.c_float)]
+lib.tb_classifier_filter_passes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
 lib.tb_classifier_filter_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
 lib.tb_classifier_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -412,12 +415,19 @@ class Classifier:
         _check(lib.tb_classifier_elapsed(self._h, slot_from, which_from, slot_to, which_to, C.byref(ms)))
         return ms.value
 
-    def rerun_resident(self, slot: int, iters: int) -> Tuple[float, float]:
+    def rerun_resident(self, slot: int, iters: int, flush_bytes: int = 0) -> Tuple[float, float]:
         """Re-run the device part of the slot's last batch `iters` times with no
-        copies; returns (total ms, ms spent in the classify kernel)."""
+        copies; returns (total ms, ms spent in the classify kernel).  With
+        flush_bytes > 0 a scratch buffer of that size is overwritten between steps."""
         total, cls = C.c_float(), C.c_float()
-        _check(lib.tb_classifier_rerun_resident(self._h, slot, iters, C.byref(total), C.byref(cls)))
+        _check(lib.tb_classifier_rerun_resident_flush(self._h, slot, iters, flush_bytes,
+                                                      C.byref(total), C.byref(cls)))
         return total.value, cls.value
+
+    def filter_passes(self, slot: int) -> int:
+        n = C.c_uint64()
+        _check(lib.tb_classifier_filter_passes(self._h, slot, C.byref(n)))
+        return n.value
 
     def filter_info(self) -> dict:
         """log2(bits) of the L2-resident pre-filter (0 = direct kernel) and its build time."""
