@@ -319,6 +319,45 @@ def run_gpu_arm(args, rank, local_rank, world):
     dist.barrier()
     e2e_ms = dist.reduce(e2e_ms, "MAX")
 
+    # ---- same batch through the host-packed entry (north_star's "pinned, 2-bit-packed
+    # ---- batches"): (a) packing timed on its own, (b) packed batches already in pinned
+    # ---- memory -> H2D of 0.25 B/base -> kernels -> D2H, (c) ASCII in, host pack INSIDE
+    # ---- the timed region, then (b)
+    host_threads = os.cpu_count() or 1
+    pbs = [kmers.PackedBatch(total, n_reads) for _ in range(2)]
+    for pb in pbs:
+        pb.pack(bases, offsets, k, threads=host_threads)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        pbs[0].pack(bases, offsets, k, threads=host_threads)
+    pack_s = (time.perf_counter() - t0) / 3
+
+    def packed_pass(n_steps, pack_inside):
+        clf.mark(0, 0)
+        for i in range(n_steps):
+            slot = i & 1
+            if i >= 2:
+                clf.wait(slot)
+            if pack_inside:
+                pbs[slot].pack(bases, offsets, k, threads=host_threads)
+            clf.submit_packed(slot, pbs[slot])
+        clf.mark(0, 1)
+        clf.mark(1, 1)
+        clf.wait(0)
+        clf.wait(1)
+        return max(clf.elapsed_ms(0, 0, 0, 1), clf.elapsed_ms(0, 0, 1, 1))
+
+    packed_pass(3, False)
+    pca, pcb, *_ = clf.result(0)
+    assert (pca == ca).all() and (pcb == cb).all(), "host-packed path differs from the ASCII path"
+    dist.barrier()
+    e2e_packed_ms = dist.reduce(packed_pass(args.steps, False), "MAX")
+    dist.barrier()
+    e2e_hostpack_ms = dist.reduce(packed_pass(max(3, args.steps // 5), True), "MAX") * args.steps / max(3, args.steps // 5)
+    # leave an ASCII batch resident in slot 0 for the device-only timing below
+    clf.submit(0, None, None, n_reads=n_reads)
+    clf.wait(0)
+
     # ---- HBM-resident: device part only, CUDA events on the slot's stream
     clf.rerun_resident(0, max(3, args.warmup))
     dist.barrier()
@@ -424,6 +463,17 @@ def run_gpu_arm(args, rank, local_rank, world):
                     "d2h_bytes_per_step": n_reads * (4 + 4 + 8 + 8 + 1),
                     "ms_per_step": e2e_ms / args.steps,
                     "api": "tb_classifier_submit/wait (C ABI), pinned host buffers, 2 slots in flight"},
+            "e2e_packed": {"value": total_all / (e2e_packed_ms / args.steps * 1e-3), "unit": UNIT,
+                           "h2d_bytes_per_step": pbs[0].h2d_bytes, "d2h_bytes_per_step": n_reads * (4 + 4 + 8 + 8 + 1),
+                           "ms_per_step": e2e_packed_ms / args.steps,
+                           "api": "tb_classifier_submit_packed: 2-bit batches packed by tb_pack_reads, already in "
+                                  "pinned host memory when the timed region starts (packing is reported in host_pack)"},
+            "e2e_ascii_hostpack": {"value": total_all / (e2e_hostpack_ms / args.steps * 1e-3), "unit": UNIT,
+                                   "ms_per_step": e2e_hostpack_ms / args.steps,
+                                   "api": "ASCII in pinned host memory -> tb_pack_reads on the host cores inside the "
+                                          "timed region -> tb_classifier_submit_packed"},
+            "host_pack": {"value": total / pack_s, "unit": UNIT, "threads": host_threads,
+                          "what": "tb_pack_reads (AVX2, multi-threaded): ASCII -> 2-bit pinned batch, this rank"},
             "gpu_launches": 5 * args.steps,
             "value_l2_flushed": total_all / (flush_ms_max / args.steps * 1e-3),
             "roofline": roofline,

@@ -141,6 +141,66 @@ int tb_classifier_submit(tb_classifier *c, int slot,
                          int32_t *count_A, int32_t *count_B,
                          double *score_A, double *score_B, char *bin);
 int tb_classifier_wait(tb_classifier *c, int slot);
+/* ---- host-packed batches (north_star: "pinned, 2-bit-packed batches") -------------
+ * tb_pack_reads converts concatenated ASCII reads into the flat 2-bit layout the
+ * classify kernels consume, on the host (multi-threaded, AVX2), so that 0.25 byte per
+ * base crosses PCIe.  All arrays are caller-owned (pinned memory from tb_host_alloc for
+ * asynchronous copies); cap_* are their capacities, the n_* fields are outputs.
+ *   F          cap_words  u64: >= (ceil(total/1024)+1)*32
+ *   dirty      cap_tiles  u32: >= ceil(total/1024)+1
+ *   dirty_idx / e_words   cap_dirty: words holding a non-ACGT byte and their fill-forward form
+ *   ub_*       reads with a non-ACGT byte among their first k bases (quirk Q3-UB): read
+ *              index, number of leading windows to replay, offset of its ASCII prefix in
+ *              ub_bytes
+ * Returns 0, -1 bad arguments, -2 F/dirty too small, -3 rare-path arrays too small. */
+typedef struct tb_packed_batch {
+    int64_t n_reads, total_bases, n_tiles;
+    uint64_t *F;
+    int64_t cap_words;
+    uint32_t *dirty;
+    int64_t cap_tiles;
+    uint32_t *dirty_idx;
+    uint64_t *e_words;
+    int64_t cap_dirty, n_dirty;
+    uint32_t *ub_read, *ub_skip;
+    int64_t *ub_off;
+    unsigned char *ub_bytes;
+    int64_t cap_ub, n_ub, cap_ub_bytes, ub_bytes_used;
+} tb_packed_batch;
+int tb_pack_reads(const char *bases, const int64_t *offsets, int64_t n_reads, int k, int n_threads,
+                  tb_packed_batch *out);
+/* Array capacities a tb_packed_batch needs to be usable with this classifier's slots. */
+int tb_classifier_capacity(tb_classifier *c, int64_t *max_bases, int64_t *max_reads, int64_t *cap_words,
+                           int64_t *cap_tiles, int64_t *cap_dirty, int64_t *cap_ub, int64_t *cap_ub_bytes);
+/* Enqueue a host-packed batch on a slot: H2D of F/dirty/offsets (+ the rare-path arrays),
+ * then index + classify + fix-up + decide and the D2H of the results, like submit(). */
+int tb_classifier_submit_packed(tb_classifier *c, int slot, const tb_packed_batch *batch,
+                                const int64_t *offsets, int32_t *count_A, int32_t *count_B,
+                                double *score_A, double *score_B, char *bin);
+
+/* ---- native streaming pipeline ---------------------------------
+ * Classify a whole FASTA/FASTQ(.gz) file: a reader thread parses records with the exact
+ * semantics of the reference's readfq (seq.py:45-83) into pinned batches, batches are
+ * classified on the GPU with two slots in flight, every record is written to the gzip file
+ * of its bin (independent gzip members compressed in parallel; the decompressed bytes
+ * equal the reference's output) and one TSV line per read (name, bin, score A, score B;
+ * classify_by_kmers.py:117, Python float repr) goes to tsv_fd (-1: none).
+ * out_a/out_b/out_u are complete file names.  Returns 0 or a negative error code. */
+typedef struct tb_stream_stats {
+    uint64_t n_reads, n_bases, n_batches, input_bytes;
+    uint64_t reads_a, reads_b, reads_u;
+    uint64_t output_raw_bytes, output_gz_bytes;
+    double seconds_total, seconds_parse, seconds_gpu_wait, seconds_write;
+} tb_stream_stats;
+int tb_classify_fastx(const char *reads_path, const hash_set *A, const hash_set *B,
+                      const char *out_a, const char *out_b, const char *out_u, int gzip_level,
+                      int tsv_fd, int64_t batch_bases, int n_threads, tb_stream_stats *stats);
+/* Python's repr(float) of x into buf (testing aid for the TSV writer). */
+int tb_float_repr(double x, char *buf, int buf_len);
+/* Parse a file with the native reader and write "name<TAB>seq<TAB>qual|<None>" per record
+ * to out_fd (testing aid; no GPU involved).  Returns the number of records or < 0. */
+int64_t tb_fastx_dump(const char *reads_path, int out_fd);
+
 /* Timing marks: record CUDA event `which` (0 or 1) on the slot's stream at the
  * current point of its queue; elapsed() waits for the `to` mark and returns the
  * device time between two marks (possibly of different slots) in milliseconds. */

@@ -426,3 +426,93 @@ def test_prefilter_does_not_change_results(kmers, oracle, k):
         else:
             os.environ["TB_FILTER_LOG2"] = old
     assert {0, 10, 20, 26} <= seen
+
+
+# ---------------------------------------------------------------- host-packed batches
+@pytest.mark.parametrize("k", [21, 32, 6])
+def test_host_packed_path_equals_ascii_path(kmers, oracle, k):
+    """tb_pack_reads (host, AVX2) + tb_classifier_submit_packed vs the ASCII submit and the
+    oracle, with non-ACGT bytes everywhere (dirty words, Q3-UB prefixes)."""
+    from trio_binning_b200 import synth
+
+    n_keys = 20000 if k > 8 else 900
+    ka, kb = synth.random_kmer_sets(n_keys, n_keys, k, seed=300 + k)
+    rng = np.random.default_rng(k)
+    bases, offsets, _ = synth.random_reads(700, 900, k, ka, kb, seed=8, plant_every=80)
+    bases = bases.copy()
+    junk = np.frombuffer(b"NnacgtRY\r\x80-", dtype=np.uint8)
+    pos = rng.integers(0, len(bases), size=len(bases) // 40)
+    bases[pos] = junk[rng.integers(0, len(junk), size=len(pos))]
+    for r in range(0, 700, 11):
+        bases[offsets[r]:min(offsets[r + 1], offsets[r] + int(rng.integers(1, 80)))] = ord("N")
+    A = kmers.create_kmer_hash_set_from_ints(ka, k)
+    B = kmers.create_kmer_hash_set_from_ints(kb, k)
+    oa, ob = oracle.set_from_ints(ka, k), oracle.set_from_ints(kb, k)
+    wa, wb = oracle.count_batch(bases, offsets, oa, ob)
+    total, n = int(offsets[-1]), len(offsets) - 1
+    with kmers.Classifier(A, B, total, n, 2) as clf:
+        pb = kmers.PackedBatch(total, n)
+        pb.pack(bases, offsets, k)
+        assert pb.c.n_ub > 0 and pb.c.n_dirty > 0
+        clf.submit_packed(0, pb)
+        clf.submit(1, bases, offsets)
+        p = clf.result(0)
+        a = clf.result(1)
+        assert (p[0] == wa).all() and (p[1] == wb).all()
+        assert (a[0] == wa).all() and (a[1] == wb).all()
+        assert (p[2] == a[2]).all() and (p[3] == a[3]).all() and (p[4] == a[4]).all()
+        # empty batch through the packed entry
+        pb.pack(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64), k)
+        clf.submit_packed(0, pb)
+        assert len(clf.result(0)[0]) == 0
+
+
+# ---------------------------------------------------------------- native pipeline vs Python I/O
+def _write_fastq(path, bases, offsets, rng, width=0):
+    import gzip as gz
+
+    quals = bytes(range(33, 74))
+    with (gz.open(path, "wb", compresslevel=1) if str(path).endswith(".gz") else open(path, "wb")) as f:
+        for r in range(len(offsets) - 1):
+            s = bytes(bases[offsets[r]:offsets[r + 1]])
+            q = bytes(rng.choice(list(quals)) for _ in range(len(s)))
+            if r % 7 == 3:  # some FASTA records in between
+                f.write(b">read%d fasta\n%s\n" % (r, s))
+            else:
+                f.write(b"@read%d some comment\n%s\n+\n%s\n" % (r, s, q))
+
+
+def test_native_pipeline_equals_python_io(kmers, capsys, tmp_path):
+    """Same input through the native pipeline (default) and the Python reader/writer
+    (--python-io): identical TSV and identical decompressed outputs, several batches."""
+    import random
+
+    from trio_binning_b200 import synth
+    from trio_binning_b200.classify_by_kmers import main
+
+    k = 21
+    ka, kb = synth.random_kmer_sets(4000, 3000, k, seed=21)
+    bases, offsets, _ = synth.random_reads(600, 1500, k, ka, kb, seed=22, plant_every=120, invalid_rate=0.002)
+    pa, pb = tmp_path / "a.txt", tmp_path / "b.txt"
+    synth.write_kmer_file(str(pa), ka, k)
+    synth.write_kmer_file(str(pb), kb, k)
+    reads = tmp_path / "reads.fastq.gz"
+    _write_fastq(reads, bases, offsets, random.Random(3))
+    outs = {}
+    for mode, extra in (("native", []), ("python", ["--python-io"])):
+        d = tmp_path / mode
+        d.mkdir()
+        argv = ["classify-by-kmers", str(reads), str(pa), str(pb), "--haplotype-a-out-prefix", str(d / "A"),
+                "--haplotype-b-out-prefix", str(d / "B"), "--unclassified-out-prefix", str(d / "U"),
+                "--batch-bases", "100000"] + extra
+        with patch("sys.argv", argv):
+            main()
+        tsv, _ = capsys.readouterr()
+        files = {n: gzip.decompress(open(d / n, "rb").read()) for n in sorted(os.listdir(d))}
+        outs[mode] = (tsv, files)
+    assert sorted(outs["native"][1]) == ["A.fastq.gz", "B.fastq.gz", "U.fastq.gz"]
+    assert outs["native"][0] == outs["python"][0]
+    assert outs["native"][1] == outs["python"][1]
+    assert outs["native"][0].count("\n") == 600
+    bins = [line.split("\t")[1] for line in outs["native"][0].splitlines()]
+    assert {"A", "B", "U"} <= set(bins)

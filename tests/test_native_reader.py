@@ -1,0 +1,97 @@
+"""The native FASTX reader and TSV float formatting of csrc/fastx_pipeline.cpp, on the CPU.
+
+Oracle: trio_binning_b200/seq.py on the same FILES (its open_fastx_read is the reference's
+call, `readfq(open(name, "r"))` / `gzip.open(name, "rt")`, so text-mode universal newlines
+apply on both sides), and seq.py itself is pinned to the reference's readfq by
+tests/test_seq.py.  Records must not contain TABs for the dump format used here."""
+import gzip
+import random
+
+import pytest
+
+
+@pytest.fixture(scope="module")
+def kmers():
+    from trio_binning_b200 import kmers as mod
+
+    return mod
+
+
+@pytest.fixture(scope="module")
+def seq():
+    from trio_binning_b200 import seq as mod
+
+    return mod
+
+
+def _python_records(seq, path):
+    return [(r.name.encode(), r.seq.encode(), None if r.qual is None else r.qual.encode())
+            for r in seq.open_fastx_read(str(path))]
+
+
+def test_native_reader_on_golden_edge_cases(kmers, seq, golden_seq, tmp_path):
+    for name, case in golden_seq.items():
+        text = case["input"].replace("\t", " ")
+        for suffix in ("", ".gz"):
+            p = tmp_path / f"{name}.fx{suffix}"
+            raw = text.encode()
+            if suffix:
+                with gzip.open(p, "wb") as f:
+                    f.write(raw)
+            else:
+                p.write_bytes(raw)
+            assert kmers.fastx_dump(str(p)) == _python_records(seq, p), (name, suffix)
+
+
+def test_native_reader_newline_flavours(kmers, seq, tmp_path):
+    cases = {
+        "crlf": b"@r1 c\r\nACGT\r\n+\r\n!!!!\r\n>r2\r\nGG\r\nTT\r\n",
+        "cr_only": b">r1\rACGT\r>r2\rGG\r",
+        "mixed": b">r1\nAC\r\nGT\rTT\n@q\nAA\n+\n!!\n",
+        "cr_at_chunk_edge": b">r1\n" + b"A" * 70 + b"\r\n" + b"C" * 10 + b"\r",
+        "utf8_name": ">résumé x\nACGT\n".encode(),
+        "fastq_no_final_newline": b"@r1\nACGT\n+\n!!!!",
+        "plus_only_at_eof": b"@r1\nACGT\n+",
+        "header_only_at_eof": b">",
+    }
+    for name, raw in cases.items():
+        p = tmp_path / f"{name}.fq"
+        p.write_bytes(raw)
+        assert kmers.fastx_dump(str(p)) == _python_records(seq, p), name
+
+
+def test_native_reader_random_files(kmers, seq, tmp_path):
+    rng = random.Random(5)
+    for trial in range(6):
+        lines = []
+        for r in range(300):
+            L = rng.randrange(0, 400)
+            s = "".join(rng.choice("ACGTNacgt") for _ in range(L))
+            width = rng.choice([60, 80, 10**9])
+            chunks = [s[i:i + width] for i in range(0, L, width)] or [""]
+            if rng.random() < 0.5:
+                lines.append(f">read{r} comment {trial}")
+                lines += chunks
+            else:
+                q = "".join(chr(rng.randrange(33, 74)) for _ in range(L))
+                lines.append(f"@read{r}")
+                lines += chunks
+                lines.append("+" if rng.random() < 0.7 else f"+read{r}")
+                lines += [q[i:i + width] for i in range(0, L, width)] or [""]
+        text = "\n".join(lines) + ("\n" if trial % 2 == 0 else "")
+        p = tmp_path / f"rand{trial}.fastq.gz"
+        with gzip.open(p, "wt") as f:
+            f.write(text)
+        got = kmers.fastx_dump(str(p))
+        assert got == _python_records(seq, p), trial
+        assert len(got) >= 299
+
+
+def test_float_repr_matches_python(kmers):
+    rng = random.Random(1)
+    values = [0.0, 1.0, 4.0, 4 / 3, 8 / 3, 1e15, 1e16, 1.5e16, 123456789012345680.0, 1e22, 1e-4, 1e-5,
+              0.00012345, 5e-324, 1.7976931348623157e308, 2.5, 100.0, 1e100, 3 * (7 / 3), 0.1 + 0.2]
+    values += [rng.randrange(0, 2**31) * (rng.randrange(1, 10**9) / rng.randrange(1, 10**9)) for _ in range(3000)]
+    values += [rng.random() * 10 ** rng.randrange(-30, 30) for _ in range(3000)]
+    for v in values:
+        assert kmers.float_repr(v) == repr(float(v)), v

@@ -12,7 +12,8 @@ from importlib.machinery import EXTENSION_SUFFIXES
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-SOURCES = ["capi.cu", "set_build.cu", "classify.cu", "gather_bench.cu"]
+SOURCES = ["capi.cu", "set_build.cu", "classify.cu", "gather_bench.cu", "host_pack.cpp",
+           "fastx_pipeline.cpp"]
 HEADERS = ["kmer_device.cuh", "launchers.h", os.path.join("..", "..", "include", "trio_kmers_b200.h")]
 LIB_NAME = "kmers_c" + EXTENSION_SUFFIXES[0]
 LIB_PATH = os.path.join(PKG, LIB_NAME)
@@ -21,8 +22,8 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
-    "-Xcompiler", "-fPIC,-O2,-Wall",
-    "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-pthread",
+    "-shared", "-cudart", "static", "-lz",
 ]
 
 

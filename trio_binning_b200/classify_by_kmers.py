@@ -69,6 +69,26 @@ def parse_args(argv=None):
         default=DEFAULT_BATCH_BASES,
         help="bases per GPU batch (B200 addition; does not change results)",
     )
+    parser.add_argument(
+        "--python-io",
+        action="store_true",
+        default=False,
+        help="read and write FASTA/FASTQ in Python like the reference instead of the native "
+        "multi-threaded pipeline (B200 addition; same output)",
+    )
+    parser.add_argument(
+        "--gzip-level",
+        type=int,
+        default=9,
+        help="compression level of the gzipped outputs; 9 is what the reference's gzip.open "
+        "uses (B200 addition; native pipeline only)",
+    )
+    parser.add_argument(
+        "--threads",
+        type=int,
+        default=0,
+        help="host threads for the native pipeline, 0 = all cores (B200 addition)",
+    )
     return parser.parse_args(argv)
 
 
@@ -95,6 +115,36 @@ def _emit(read, result, files, out):
     print("\t".join(map(str, [read.name, read_bin, score_a, score_b])), file=out)
 
 
+def _main_native(args):
+    """gzip outputs on one GPU: the whole loop (parse, batch, classify, route, compress, TSV)
+    runs in the native pipeline (csrc/fastx_pipeline.cpp); file names follow the reference."""
+    extension = path.splitext(args.reads.rstrip(".gz"))[1]  # reference :90 (quirk Q8)
+    names = [prefix + extension + ".gz" for prefix in
+             (args.haplotype_a_out_prefix, args.haplotype_b_out_prefix, args.unclassified_out_prefix)]
+    sys.stdout.flush()
+    try:
+        fd = sys.stdout.fileno()
+        borrowed = None
+    except (AttributeError, OSError, ValueError):
+        # stdout is not a real file (captured): collect the TSV in a temporary file
+        import tempfile
+
+        borrowed = tempfile.TemporaryFile()
+        fd = borrowed.fileno()
+    stats = kmers.classify_fastx_file(args.reads, args.haplotype_a_kmers, args.haplotype_b_kmers,
+                                      names[0], names[1], names[2], tsv_fd=fd,
+                                      gzip_level=args.gzip_level, batch_bases=args.batch_bases,
+                                      threads=args.threads)
+    if os.environ.get("TB_VERBOSE"):
+        print("[tb] native pipeline: " + ", ".join(f"{k}={v:.3f}" if isinstance(v, float) else f"{k}={v}"
+                                                   for k, v in stats.items()), file=sys.stderr)
+    if borrowed is not None:
+        borrowed.seek(0)
+        sys.stdout.write(borrowed.read().decode("utf-8"))
+        borrowed.close()
+    return stats
+
+
 def main(argv=None):
     """Main method of program"""
     # Under torchrun (WORLD_SIZE > 1) every rank drives its own GPU; the sets are built
@@ -105,6 +155,10 @@ def main(argv=None):
     comm = sharding.Communicator.from_env()
 
     args = parse_args(argv)
+
+    if not args.no_gzip_output and not args.python_io and comm.world == 1:
+        _main_native(args)
+        return
 
     reads = seq.open_fastx_read(args.reads)
 

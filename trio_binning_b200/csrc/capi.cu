@@ -281,6 +281,12 @@ struct Slot {
              *d_ub_list = nullptr;
     unsigned int *d_ub_count = nullptr;
     unsigned long long *d_n_pass = nullptr;
+    // rare-path arrays of host-packed batches
+    uint32_t *d_dirty_idx = nullptr, *d_ub_read = nullptr, *d_ub_skip = nullptr;
+    uint64_t *d_e_words = nullptr;
+    int64_t *d_ub_off = nullptr;
+    unsigned char *d_ub_bytes = nullptr;
+    int64_t cap_dirty = 0, cap_ub = 0, cap_ub_bytes = 0;
     int32_t *d_ca = nullptr, *d_cb = nullptr;
     double *d_sa = nullptr, *d_sb = nullptr;
     char *d_bin = nullptr;
@@ -312,7 +318,8 @@ namespace {
 void free_slot(Slot &s)
 {
     void *ptrs[] = { s.d_ascii, s.d_offsets, s.d_F, s.d_E, s.d_dirty, s.d_tile_first, s.d_flags,
-                     s.d_skip, s.d_ub_list, s.d_ub_count, s.d_n_pass, s.d_ca, s.d_cb, s.d_sa, s.d_sb, s.d_bin };
+                     s.d_skip, s.d_ub_list, s.d_ub_count, s.d_n_pass, s.d_dirty_idx, s.d_ub_read, s.d_ub_skip,
+                     s.d_e_words, s.d_ub_off, s.d_ub_bytes, s.d_ca, s.d_cb, s.d_sa, s.d_sb, s.d_bin };
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; i++) {
@@ -349,6 +356,15 @@ int alloc_slot(Slot &s, int64_t max_bases, int64_t max_reads)
     CK(cudaMalloc((void **)&s.d_sa, (size_t)(max_reads + 1) * 8));
     CK(cudaMalloc((void **)&s.d_sb, (size_t)(max_reads + 1) * 8));
     CK(cudaMalloc((void **)&s.d_bin, (size_t)(max_reads + 1)));
+    s.cap_dirty = words;  // worst case: every word holds a non-ACGT byte
+    s.cap_ub = max_reads + 1;
+    s.cap_ub_bytes = std::max<int64_t>(1 << 20, max_bases / 16);
+    CK(cudaMalloc((void **)&s.d_dirty_idx, (size_t)s.cap_dirty * 4));
+    CK(cudaMalloc((void **)&s.d_e_words, (size_t)s.cap_dirty * 8));
+    CK(cudaMalloc((void **)&s.d_ub_read, (size_t)s.cap_ub * 4));
+    CK(cudaMalloc((void **)&s.d_ub_skip, (size_t)s.cap_ub * 4));
+    CK(cudaMalloc((void **)&s.d_ub_off, (size_t)(s.cap_ub + 1) * 8));
+    CK(cudaMalloc((void **)&s.d_ub_bytes, (size_t)s.cap_ub_bytes + 64));
     CK(cudaMemset(s.d_flags, 0, (size_t)(max_reads + 1) * 4));
     CK(cudaMemset(s.d_ub_count, 0, 2 * sizeof(unsigned int)));
     CK(cudaMemset(s.d_E, 0, (size_t)words * 8));
@@ -682,6 +698,8 @@ int tb_classifier_submit(tb_classifier *c, int slot, const char *bases, const in
     v.ub_list = s.d_ub_list;
     v.ub_count = s.d_ub_count;
     v.n_pass = s.d_n_pass;
+    v.ub_ascii = nullptr;
+    v.ub_ascii_off = nullptr;
     v.count_a = s.d_ca;
     v.count_b = s.d_cb;
     v.score_a = score_A ? s.d_sa : nullptr;
@@ -700,6 +718,99 @@ int tb_classifier_submit(tb_classifier *c, int slot, const char *bases, const in
     if (score_A) CK(cudaMemcpyAsync(score_A, s.d_sa, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, s.stream));
     if (score_B) CK(cudaMemcpyAsync(score_B, s.d_sb, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, s.stream));
     if (bin) CK(cudaMemcpyAsync(bin, s.d_bin, (size_t)n_reads, cudaMemcpyDeviceToHost, s.stream));
+    return 0;
+}
+
+int tb_classifier_capacity(tb_classifier *c, int64_t *max_bases, int64_t *max_reads, int64_t *cap_words,
+                           int64_t *cap_tiles, int64_t *cap_dirty, int64_t *cap_ub, int64_t *cap_ub_bytes)
+{
+    if (!c) return fail("null classifier");
+    const Slot &s = c->slots[0];
+    const int64_t tiles = (c->max_bases + 1023) / 1024;
+    if (max_bases) *max_bases = c->max_bases;
+    if (max_reads) *max_reads = c->max_reads;
+    if (cap_words) *cap_words = (tiles + 1) * 32;
+    if (cap_tiles) *cap_tiles = tiles + 1;
+    if (cap_dirty) *cap_dirty = s.cap_dirty;
+    if (cap_ub) *cap_ub = s.cap_ub;
+    if (cap_ub_bytes) *cap_ub_bytes = s.cap_ub_bytes;
+    return 0;
+}
+
+int tb_classifier_submit_packed(tb_classifier *c, int slot, const tb_packed_batch *pb,
+                                const int64_t *offsets, int32_t *count_A, int32_t *count_B,
+                                double *score_A, double *score_B, char *bin)
+{
+    if (!c || !pb) return fail("null classifier / batch");
+    if (slot < 0 || slot >= (int)c->slots.size()) return fail("slot %d out of range", slot);
+    if (!count_A || !count_B) return fail("count_A / count_B must not be NULL");
+    const int64_t n_reads = pb->n_reads, total = pb->total_bases;
+    if (n_reads < 0 || n_reads > c->max_reads || total > c->max_bases)
+        return fail("packed batch (%lld reads, %lld bases) exceeds classifier capacity",
+                    (long long)n_reads, (long long)total);
+    CK(cudaSetDevice(c->device));
+    Slot &s = c->slots[(size_t)slot];
+    if (pb->n_dirty > s.cap_dirty || pb->n_ub > s.cap_ub || pb->ub_bytes_used > s.cap_ub_bytes)
+        return fail("packed batch has too many non-ACGT words for the slot; use the ASCII submit");
+    uint64_t windows = 0;
+    for (int64_t r = 0; r < n_reads; r++) {
+        int64_t len = offsets[r + 1] - offsets[r];
+        if (len >= c->k) windows += (uint64_t)(len - c->k + 1);
+    }
+    tb_batch_view &v = s.view;
+    v.ascii = nullptr;
+    v.offsets = s.d_offsets;
+    v.n_reads = n_reads;
+    v.total_bases = total;
+    v.n_tiles = pb->n_tiles;
+    v.F = s.d_F;
+    v.E = s.d_E;
+    v.dirty = s.d_dirty;
+    v.tile_first_read = s.d_tile_first;
+    v.flags = s.d_flags;
+    v.skip = s.d_skip;
+    v.ub_list = s.d_ub_list;
+    v.ub_count = s.d_ub_count;
+    v.n_pass = s.d_n_pass;
+    v.ub_ascii = s.d_ub_bytes;
+    v.ub_ascii_off = s.d_ub_off;
+    v.count_a = s.d_ca;
+    v.count_b = s.d_cb;
+    v.score_a = score_A ? s.d_sa : nullptr;
+    v.score_b = score_B ? s.d_sb : nullptr;
+    v.bin = bin ? s.d_bin : nullptr;
+    s.windows = windows;
+    s.h_ca = count_A;
+    s.has_batch = false;  // no ASCII on the device: rerun_resident needs an ASCII batch
+    if (n_reads == 0) return 0;
+    cudaStream_t st = s.stream;
+    CK(cudaMemcpyAsync(s.d_F, pb->F, (size_t)(pb->n_tiles + 1) * 32 * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.d_dirty, pb->dirty, (size_t)(pb->n_tiles + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.d_offsets, offsets, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (pb->n_dirty) {
+        CK(cudaMemcpyAsync(s.d_dirty_idx, pb->dirty_idx, (size_t)pb->n_dirty * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.d_e_words, pb->e_words, (size_t)pb->n_dirty * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (pb->n_ub) {
+        CK(cudaMemcpyAsync(s.d_ub_read, pb->ub_read, (size_t)pb->n_ub * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.d_ub_skip, pb->ub_skip, (size_t)pb->n_ub * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.d_ub_off, pb->ub_off, (size_t)pb->n_ub * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.d_ub_bytes, pb->ub_bytes, (size_t)pb->ub_bytes_used, cudaMemcpyHostToDevice, st));
+    }
+    const tb_set_view A = view_of(c->A), B = view_of(c->B);
+    CK(tb_launch_index_packed(v, s.d_dirty_idx, s.d_e_words, pb->n_dirty, s.d_ub_read, s.d_ub_skip,
+                              pb->n_ub, st));
+    if (c->d_filter)
+        CK(tb_launch_classify_filtered(v, c->k, A, B, c->d_filter, c->filter_mask, st));
+    else
+        CK(tb_launch_classify(v, c->k, A, B, st));
+    CK(tb_launch_fixup(v, c->k, A, B, st));
+    CK(tb_launch_finalize(v, c->scale_a, c->scale_b, st));
+    CK(cudaMemcpyAsync(count_A, s.d_ca, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(count_B, s.d_cb, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
+    if (score_A) CK(cudaMemcpyAsync(score_A, s.d_sa, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, st));
+    if (score_B) CK(cudaMemcpyAsync(score_B, s.d_sb, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, st));
+    if (bin) CK(cudaMemcpyAsync(bin, s.d_bin, (size_t)n_reads, cudaMemcpyDeviceToHost, st));
     return 0;
 }
 

@@ -175,6 +175,39 @@ k_index(tb_batch_view b, int k)
 }
 
 // ============================================================================
+// host-packed batches: the work k_pack/k_index did from ASCII arrives precomputed
+// (host_pack.cpp); what is left is the tile map, zeroed counters, scattering the few
+// fill-forward words and installing the Q3-UB list.
+// ============================================================================
+__global__ void __launch_bounds__(256)
+k_index_packed(tb_batch_view b)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) *b.n_pass = 0;
+    if (r >= b.n_reads) return;
+    const int64_t start = b.offsets[r], end = b.offsets[r + 1];
+    for (int64_t t = (start + 1023) >> 10; (t << 10) < end; t++)
+        b.tile_first_read[t] = (uint32_t)r;
+    b.count_a[r] = 0;
+    b.count_b[r] = 0;
+    b.skip[r] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_apply_rare(tb_batch_view b, const uint32_t *__restrict__ dirty_idx,
+             const uint64_t *__restrict__ e_words, int64_t n_dirty,
+             const uint32_t *__restrict__ ub_read, const uint32_t *__restrict__ ub_skip, int64_t n_ub)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_dirty) b.E[dirty_idx[i]] = e_words[i];
+    if (i < n_ub) {
+        b.skip[ub_read[i]] = ub_skip[i];
+        b.ub_list[i] = ub_read[i];
+    }
+    if (i == 0) *b.ub_count = (unsigned)n_ub;
+}
+
+// ============================================================================
 // k_classify (direct) and k_classify_filtered (L2-resident pre-filter)
 // ============================================================================
 
@@ -482,7 +515,7 @@ k_fixup(tb_batch_view b, int k, tb_set_view A, tb_set_view B)
     const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t r = b.ub_list[i];
-        const unsigned char *read = b.ascii + b.offsets[r];
+        const unsigned char *read = b.ub_ascii_off ? b.ub_ascii + b.ub_ascii_off[i] : b.ascii + b.offsets[r];
         const uint32_t skip = b.skip[r];
         uint64_t rc = 0;  // sticky digits, slot s at bits 2s, zero-initialised
         int ca = 0, cb = 0;
@@ -584,6 +617,19 @@ cudaError_t tb_launch_index(const tb_batch_view &b, int k, cudaStream_t stream)
 {
     if (b.n_reads == 0) return cudaSuccess;
     k_index<<<(unsigned)((b.n_reads + 255) / 256), 256, 0, stream>>>(b, k);
+    return cudaGetLastError();
+}
+
+cudaError_t tb_launch_index_packed(const tb_batch_view &b, const uint32_t *d_dirty_idx,
+                                   const uint64_t *d_e_words, int64_t n_dirty, const uint32_t *d_ub_read,
+                                   const uint32_t *d_ub_skip, int64_t n_ub, cudaStream_t stream)
+{
+    if (b.n_reads == 0) return cudaSuccess;
+    k_index_packed<<<(unsigned)((b.n_reads + 255) / 256), 256, 0, stream>>>(b);
+    const int64_t n = n_dirty > n_ub ? n_dirty : n_ub;
+    // always launched (n >= 1 thread) so that ub_count is set even when nothing is rare
+    k_apply_rare<<<(unsigned)((n + 256) / 256), 256, 0, stream>>>(b, d_dirty_idx, d_e_words, n_dirty,
+                                                                 d_ub_read, d_ub_skip, n_ub);
     return cudaGetLastError();
 }
 

@@ -44,6 +44,11 @@ struct tb_batch_view {
     uint32_t *ub_list;
     unsigned int *ub_count;  // device counter; zero before the batch, reset by finalize
     unsigned long long *n_pass;  // windows that passed the pre-filter (reset by k_index)
+    // Q3-UB replay source: by default the batch's own ASCII (read r starts at offsets[r]);
+    // host-packed batches carry only the prefixes k_fixup needs: entry i of ub_list reads
+    // ub_ascii + ub_ascii_off[i]
+    const unsigned char *ub_ascii;
+    const int64_t *ub_ascii_off;
     int32_t *count_a;
     int32_t *count_b;
     double *score_a;
@@ -53,6 +58,10 @@ struct tb_batch_view {
 
 cudaError_t tb_launch_pack(const tb_batch_view &b, int k, cudaStream_t stream);
 cudaError_t tb_launch_index(const tb_batch_view &b, int k, cudaStream_t stream);
+// host-packed batches: index without ASCII, scatter of the dirty E words, Q3-UB list from the host
+cudaError_t tb_launch_index_packed(const tb_batch_view &b, const uint32_t *d_dirty_idx,
+                                   const uint64_t *d_e_words, int64_t n_dirty, const uint32_t *d_ub_read,
+                                   const uint32_t *d_ub_skip, int64_t n_ub, cudaStream_t stream);
 cudaError_t tb_launch_classify(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
                                cudaStream_t stream);
 // filtered variant: `filter` is a bitmap of filter_mask+1 bits over the keys of A and B

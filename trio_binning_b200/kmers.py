@@ -140,6 +140,46 @@ lib.tb_gather_bench.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, 
                                 C.POINTER(C.c_double), C.POINTER(C.c_float)]
 
 
+class _PackedBatch(C.Structure):
+    """`tb_packed_batch` of include/trio_kmers_b200.h."""
+
+    _fields_ = [
+        ("n_reads", C.c_int64), ("total_bases", C.c_int64), ("n_tiles", C.c_int64),
+        ("F", C.c_void_p), ("cap_words", C.c_int64),
+        ("dirty", C.c_void_p), ("cap_tiles", C.c_int64),
+        ("dirty_idx", C.c_void_p), ("e_words", C.c_void_p),
+        ("cap_dirty", C.c_int64), ("n_dirty", C.c_int64),
+        ("ub_read", C.c_void_p), ("ub_skip", C.c_void_p), ("ub_off", C.c_void_p),
+        ("ub_bytes", C.c_void_p),
+        ("cap_ub", C.c_int64), ("n_ub", C.c_int64), ("cap_ub_bytes", C.c_int64),
+        ("ub_bytes_used", C.c_int64),
+    ]
+
+
+lib.tb_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(_PackedBatch)]
+lib.tb_classifier_capacity.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 7
+lib.tb_classifier_submit_packed.argtypes = [C.c_void_p, C.c_int, C.POINTER(_PackedBatch), C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+
+
+class StreamStats(C.Structure):
+    """`tb_stream_stats` of include/trio_kmers_b200.h."""
+
+    _fields_ = [(n, C.c_uint64) for n in ("n_reads", "n_bases", "n_batches", "input_bytes", "reads_a",
+                                          "reads_b", "reads_u", "output_raw_bytes", "output_gz_bytes")] + \
+               [(n, C.c_double) for n in ("seconds_total", "seconds_parse", "seconds_gpu_wait", "seconds_write")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+lib.tb_classify_fastx.argtypes = [C.c_char_p, HashSet, HashSet, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int,
+                                  C.c_int, C.c_int64, C.c_int, C.POINTER(StreamStats)]
+lib.tb_float_repr.argtypes = [C.c_double, C.c_char_p, C.c_int]
+lib.tb_fastx_dump.argtypes = [C.c_char_p, C.c_int]
+lib.tb_fastx_dump.restype = C.c_int64
+
+
 def _error() -> str:
     return (lib.tb_last_error() or b"unknown error").decode("utf-8", "replace")
 
@@ -344,6 +384,64 @@ class PinnedBuffer:
             pass
 
 
+class PackedBatch:
+    """Host-side 2-bit packed batch in pinned memory (tb_packed_batch) plus its packer.
+
+    `pack(bases, offsets, k)` runs the multi-threaded AVX2 host packer (host_pack.cpp);
+    the arrays are then ready for `Classifier.submit_packed`."""
+
+    def __init__(self, max_bases: int, max_reads: int, pinned: bool = True):
+        tiles = (int(max_bases) + 1023) // 1024
+        self.cap = dict(words=(tiles + 1) * 32, tiles=tiles + 1,
+                        dirty=(tiles + 1) * 32, ub=int(max_reads) + 1,
+                        ub_bytes=max(1 << 20, int(max_bases) // 16))
+        alloc = (lambda n, dt: PinnedBuffer(n, dt)) if pinned else (lambda n, dt: _Plain(n, dt))
+        self.F = alloc(self.cap["words"], np.uint64)
+        self.dirty = alloc(self.cap["tiles"], np.uint32)
+        self.dirty_idx = alloc(self.cap["dirty"], np.uint32)
+        self.e_words = alloc(self.cap["dirty"], np.uint64)
+        self.ub_read = alloc(self.cap["ub"], np.uint32)
+        self.ub_skip = alloc(self.cap["ub"], np.uint32)
+        self.ub_off = alloc(self.cap["ub"] + 1, np.int64)
+        self.ub_bytes = alloc(self.cap["ub_bytes"], np.uint8)
+        self.offsets = alloc(int(max_reads) + 1, np.int64)
+        self.c = _PackedBatch()
+        self.c.F, self.c.cap_words = self.F.ptr, self.cap["words"]
+        self.c.dirty, self.c.cap_tiles = self.dirty.ptr, self.cap["tiles"]
+        self.c.dirty_idx, self.c.e_words, self.c.cap_dirty = self.dirty_idx.ptr, self.e_words.ptr, self.cap["dirty"]
+        self.c.ub_read, self.c.ub_skip, self.c.ub_off = self.ub_read.ptr, self.ub_skip.ptr, self.ub_off.ptr
+        self.c.ub_bytes, self.c.cap_ub, self.c.cap_ub_bytes = self.ub_bytes.ptr, self.cap["ub"], self.cap["ub_bytes"]
+
+    def pack(self, bases: np.ndarray, offsets: np.ndarray, k: int, threads: int = 0) -> None:
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        n = len(offsets) - 1
+        self.offsets.array[: n + 1] = offsets
+        rc = lib.tb_pack_reads(bases.ctypes.data, self.offsets.ptr, n, k, threads, C.byref(self.c))
+        if rc != 0:
+            raise RuntimeError(f"tb_pack_reads failed with code {rc}")
+
+    @property
+    def n_reads(self) -> int:
+        return int(self.c.n_reads)
+
+    @property
+    def h2d_bytes(self) -> int:
+        c = self.c
+        return int((c.n_tiles + 1) * 32 * 8 + (c.n_tiles + 1) * 4 + (c.n_reads + 1) * 8 + c.n_dirty * 12
+                   + c.n_ub * 16 + c.ub_bytes_used)
+
+
+class _Plain:
+    """Pageable stand-in for PinnedBuffer (lets the packer be tested without a GPU)."""
+
+    def __init__(self, n_items, dtype):
+        self.array = np.zeros(max(1, int(n_items)), dtype=dtype)
+        self.ptr = self.array.ctypes.data
+
+    def free(self):
+        pass
+
+
 class Classifier:
     """Double-buffered asynchronous classifier (tb_classifier_* of the C ABI).
 
@@ -393,6 +491,16 @@ class Classifier:
         s["scores"] = want_scores
         _check(lib.tb_classifier_submit(
             self._h, slot, s["bases"].ptr, s["offsets"].ptr, s["n"], s["ca"].ptr, s["cb"].ptr,
+            s["sa"].ptr if want_scores else None, s["sb"].ptr if want_scores else None,
+            s["bins"].ptr if want_scores else None))
+
+    def submit_packed(self, slot: int, batch: "PackedBatch", want_scores: bool = True) -> None:
+        """Enqueue a host-packed batch (PackedBatch.pack) on a slot."""
+        s = self._slots[slot]
+        s["n"] = batch.n_reads
+        s["scores"] = want_scores
+        _check(lib.tb_classifier_submit_packed(
+            self._h, slot, C.byref(batch.c), batch.offsets.ptr, s["ca"].ptr, s["cb"].ptr,
             s["sa"].ptr if want_scores else None, s["sb"].ptr if want_scores else None,
             s["bins"].ptr if want_scores else None))
 
@@ -460,6 +568,48 @@ class Classifier:
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+
+def classify_fastx_file(reads_path: str, kmers_hap_a: "HashSet", kmers_hap_b: "HashSet", out_a: str,
+                        out_b: str, out_u: str, tsv_fd: int = -1, gzip_level: int = 9,
+                        batch_bases: int = 256 << 20, threads: int = 0) -> dict:
+    """Native streaming pipeline (tb_classify_fastx): parse, classify on the GPU, write the
+    three gzip outputs and the TSV.  Returns the pipeline's counters and stage timings."""
+    stats = StreamStats()
+    rc = lib.tb_classify_fastx(os.fsencode(reads_path), kmers_hap_a, kmers_hap_b, os.fsencode(out_a),
+                               os.fsencode(out_b), os.fsencode(out_u), gzip_level, tsv_fd, batch_bases,
+                               threads, C.byref(stats))
+    if rc != 0:
+        raise RuntimeError(f"tb_classify_fastx failed ({rc}): {_error()}")
+    return stats.as_dict()
+
+
+def float_repr(x: float) -> str:
+    """The native TSV writer's rendering of a float (must equal Python's repr)."""
+    buf = C.create_string_buffer(64)
+    n = lib.tb_float_repr(x, buf, 64)
+    if n < 0:
+        raise RuntimeError("tb_float_repr: buffer too small")
+    return buf.value.decode()
+
+
+def fastx_dump(reads_path: str):
+    """Records of a FASTA/FASTQ(.gz) file as parsed by the native reader: a list of
+    (name, seq, qual-or-None) byte strings (testing aid, no GPU needed)."""
+    import tempfile
+
+    with tempfile.TemporaryFile() as tmp:
+        n = lib.tb_fastx_dump(os.fsencode(reads_path), tmp.fileno())
+        if n < 0:
+            raise RuntimeError(f"tb_fastx_dump failed ({n})")
+        tmp.seek(0)
+        data = tmp.read()
+    out = []
+    for line in data.split(b"\n")[:-1]:
+        name, seq, qual = line.split(b"\t")[0], line.split(b"\t")[1], line.split(b"\t", 2)[2]
+        out.append((name, seq, None if qual == b"<None>" else qual))
+    assert len(out) == n
+    return out
 
 
 def gather_bench(table_bytes: int, loads_in_flight: int = 8, threads_per_block: int = 256,
