@@ -392,17 +392,21 @@ def run_gpu_arm(args, rank, local_rank, world):
             ceil_l2 = max(kmers.gather_bench(32 << 20, mlp, tpb, bps, 256, 0)[0]
                           for mlp, tpb, bps in ((8, 256, 8), (16, 256, 4), (8, 128, 16)))
         if finfo["log2_bits"]:
-            # filtered kernel: one L2 sector request per window (bitmap) + two HBM sector
-            # requests (A and B bucket) per window that passed the bitmap
-            table_probes = 2 * passes
+            # filtered kernels: one L2 sector request per window (bitmap) + one (pair table) or
+            # two (A and B) HBM sector requests per window that passed the bitmap
+            pair = finfo["pair_buckets"] > 0
+            table_probes = passes if pair else 2 * passes
             sector_requests = windows + table_probes
             algo_bytes = 32.0 * sector_requests + 0.25 * total
             achieved = algo_bytes / cls_s / 1e9
             roofline = {
-                "bound": "l2", "kernel": f"k_classify_filtered<{k},16>",
-                "note": "the bitmap pre-filter (2^%d bits, L2-resident, evict_last) answers %.1f%% of the windows "
-                        "without touching HBM; the kernel is bound by L2 sector requests (1 per SM per clock), "
-                        "not by HBM -- see hbm{} for the HBM side" % (finfo["log2_bits"], 100.0 * (1 - passes / max(1, windows))),
+                "bound": "l2",
+                "kernel": f"k_classify_pair<{k},16,{finfo['bits_per_key']}>" if pair else f"k_classify_filtered<{k},16>",
+                "note": "the bitmap pre-filter (2^%d bits, %d bit(s) per key, L2-resident, evict_last) answers %.2f%% of "
+                        "the windows without touching HBM; survivors read %s; the kernel is bound by L2 sector "
+                        "requests (1 per SM per clock), not by HBM -- see hbm{} for the HBM side"
+                        % (finfo["log2_bits"], finfo["bits_per_key"], 100.0 * (1 - passes / max(1, windows)),
+                           "one bucket of the tagged A+B pair table" if pair else "one bucket of A and one of B"),
                 "achieved": achieved,
                 "peak": (ceil_l2 * 32 / 1e9) if ceil_l2 else None,
                 "unit": "GB/s", "frac": (achieved / (ceil_l2 * 32 / 1e9)) if ceil_l2 else None,

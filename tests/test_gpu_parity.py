@@ -407,25 +407,34 @@ def test_prefilter_does_not_change_results(kmers, oracle, k):
     B = kmers.create_kmer_hash_set_from_ints(kb, k)
     oa, ob = oracle.set_from_ints(ka, k), oracle.set_from_ints(kb, k)
     wa, wb = oracle.count_batch(bases, offsets, oa, ob)
-    seen = set()
-    old = os.environ.get("TB_FILTER_LOG2")
+    seen, pair_seen = set(), set()
+    saved = {v: os.environ.get(v) for v in ("TB_FILTER_LOG2", "TB_PAIR", "TB_FILTER_BITS")}
     try:
-        for setting in ("0", "10", "20", "26", None):
-            if setting is None:
-                os.environ.pop("TB_FILTER_LOG2", None)
-            else:
-                os.environ["TB_FILTER_LOG2"] = setting
-            with kmers.Classifier(A, B, int(offsets[-1]), len(offsets) - 1, 1) as clf:
-                seen.add(clf.filter_info()["log2_bits"])
-                clf.submit(0, bases, offsets)
-                ca, cb, *_ = clf.result(0)
-                assert (ca == wa).all() and (cb == wb).all(), setting
+        for pair, bits in (("0", "1"), ("1", "1"), ("1", "2")):
+            os.environ["TB_PAIR"], os.environ["TB_FILTER_BITS"] = pair, bits
+            for setting in ("0", "10", "20", "26", None):
+                if setting is None:
+                    os.environ.pop("TB_FILTER_LOG2", None)
+                else:
+                    os.environ["TB_FILTER_LOG2"] = setting
+                with kmers.Classifier(A, B, int(offsets[-1]), len(offsets) - 1, 1) as clf:
+                    info = clf.filter_info()
+                    seen.add(info["log2_bits"])
+                    pair_seen.add((info["pair_buckets"] > 0, info["bits_per_key"]))
+                    clf.submit(0, bases, offsets)
+                    ca, cb, *_ = clf.result(0)
+                    assert (ca == wa).all() and (cb == wb).all(), (pair, bits, setting)
     finally:
-        if old is None:
-            os.environ.pop("TB_FILTER_LOG2", None)
-        else:
-            os.environ["TB_FILTER_LOG2"] = old
+        for v, val in saved.items():
+            if val is None:
+                os.environ.pop(v, None)
+            else:
+                os.environ[v] = val
     assert {0, 10, 20, 26} <= seen
+    if k <= 31:
+        assert {(False, 1), (True, 1), (True, 2)} <= pair_seen  # the pair table needs k <= 31
+    else:
+        assert pair_seen == {(False, 1)}
 
 
 # ---------------------------------------------------------------- host-packed batches

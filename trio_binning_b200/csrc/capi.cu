@@ -311,6 +311,11 @@ struct tb_classifier {
     uint32_t filter_mask = 0;
     int filter_log2 = 0;
     float filter_build_ms = 0;
+    // pair table (both sets, tagged; k <= 31): phase 2 needs one HBM bucket per window
+    tb_bucket *d_pair = nullptr;
+    uint32_t pair_buckets = 0;
+    uint64_t pair_distinct = 0;
+    int filter_bits = 1;
 };
 
 namespace {
@@ -378,7 +383,10 @@ int enqueue_kernels(tb_classifier *c, Slot &s, cudaEvent_t before_classify, cuda
     CK(tb_launch_pack(s.view, c->k, s.stream));
     CK(tb_launch_index(s.view, c->k, s.stream));
     if (before_classify) CK(cudaEventRecord(before_classify, s.stream));
-    if (c->d_filter)
+    if (c->d_pair && c->d_filter) {
+        tb_pair_view P = { c->d_pair, c->pair_buckets };
+        CK(tb_launch_classify_pair(s.view, c->k, P, c->d_filter, c->filter_mask >> 5, c->filter_bits, s.stream));
+    } else if (c->d_filter)
         CK(tb_launch_classify_filtered(s.view, c->k, A, B, c->d_filter, c->filter_mask, s.stream));
     else
         CK(tb_launch_classify(s.view, c->k, A, B, s.stream));
@@ -416,10 +424,32 @@ int build_filter(tb_classifier *c)
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, 0));
-    CK(tb_launch_filter_build(c->A->d_table, (uint64_t)c->A->n_buckets * TB_SLOTS, c->d_filter,
-                              c->filter_mask, 0));
-    CK(tb_launch_filter_build(c->B->d_table, (uint64_t)c->B->n_buckets * TB_SLOTS, c->d_filter,
-                              c->filter_mask, 0));
+    const uint64_t slots_a = (uint64_t)c->A->n_buckets * TB_SLOTS, slots_b = (uint64_t)c->B->n_buckets * TB_SLOTS;
+    if (c->k <= 31 && env_int("TB_PAIR", 1) != 0) {
+        // one tagged table for both sets
+        const uint64_t n = c->A->n_distinct + c->B->n_distinct;
+        const uint64_t nb = (uint64_t)((double)n / (TB_SLOTS * g_load_factor)) + 1;
+        if (nb > 0xFFFFFFF0ull) return fail("pair table too large");
+        c->pair_buckets = (uint32_t)nb;
+        CK(cudaMalloc((void **)&c->d_pair, nb * sizeof(tb_bucket)));
+        CK(cudaMemset(c->d_pair, 0, nb * sizeof(tb_bucket)));
+        Counters cnt;
+        if (cnt.init()) return -1;
+        CK(tb_launch_pair_insert(c->A->d_table, slots_a, 1, c->d_pair, c->pair_buckets, cnt.d, 0));
+        CK(tb_launch_pair_insert(c->B->d_table, slots_b, 2, c->d_pair, c->pair_buckets, cnt.d, 0));
+        unsigned long long cc[4];
+        if (cnt.read(cc)) return -1;
+        c->pair_distinct = cc[0];
+        // two bits per key while the bitmap stays sparse (fewer false positives for free)
+        int nbits = env_int("TB_FILTER_BITS", 0);
+        if (nbits != 1 && nbits != 2) nbits = ((double)n / (double)bits < 0.4) ? 2 : 1;
+        c->filter_bits = nbits;
+        CK(tb_launch_pair_filter_build(reinterpret_cast<const uint64_t *>(c->d_pair), nb * TB_SLOTS,
+                                       c->d_filter, c->filter_mask >> 5, nbits, 0));
+    } else {
+        CK(tb_launch_filter_build(c->A->d_table, slots_a, c->d_filter, c->filter_mask, 0));
+        CK(tb_launch_filter_build(c->B->d_table, slots_b, c->d_filter, c->filter_mask, 0));
+    }
     CK(cudaEventRecord(e1, 0));
     CK(cudaEventSynchronize(e1));
     CK(cudaEventElapsedTime(&c->filter_build_ms, e0, e1));
@@ -656,6 +686,7 @@ void tb_classifier_destroy(tb_classifier *c)
         free_slot(s);
     }
     if (c->d_filter) cudaFree(c->d_filter);
+    if (c->d_pair) cudaFree(c->d_pair);
     delete c;
 }
 
@@ -800,7 +831,10 @@ int tb_classifier_submit_packed(tb_classifier *c, int slot, const tb_packed_batc
     const tb_set_view A = view_of(c->A), B = view_of(c->B);
     CK(tb_launch_index_packed(v, s.d_dirty_idx, s.d_e_words, pb->n_dirty, s.d_ub_read, s.d_ub_skip,
                               pb->n_ub, st));
-    if (c->d_filter)
+    if (c->d_pair && c->d_filter) {
+        tb_pair_view P = { c->d_pair, c->pair_buckets };
+        CK(tb_launch_classify_pair(v, c->k, P, c->d_filter, c->filter_mask >> 5, c->filter_bits, st));
+    } else if (c->d_filter)
         CK(tb_launch_classify_filtered(v, c->k, A, B, c->d_filter, c->filter_mask, st));
     else
         CK(tb_launch_classify(v, c->k, A, B, st));
@@ -928,6 +962,15 @@ int tb_classifier_stats(tb_classifier *c, int slot, uint64_t *n_windows, uint64_
         *n_fixup_reads = n;
     }
     if (n_kernel_launches) *n_kernel_launches = s.view.n_reads ? 5 : 0;
+    return 0;
+}
+
+int tb_classifier_pair_info(tb_classifier *c, uint32_t *n_buckets, uint64_t *n_distinct, int *filter_bits)
+{
+    if (!c) return fail("null classifier");
+    if (n_buckets) *n_buckets = c->d_pair ? c->pair_buckets : 0;
+    if (n_distinct) *n_distinct = c->pair_distinct;
+    if (filter_bits) *filter_bits = c->filter_bits;
     return 0;
 }
 

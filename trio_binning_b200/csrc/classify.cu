@@ -488,6 +488,104 @@ k_classify_filtered(tb_batch_view b, int k_runtime, tb_set_view A, tb_set_view B
     lane_attribute(b, c, lane, hit_a, hit_b);
 }
 
+// ---- pair kernel -----------------------------------------------------------------------
+// Same two phases, with (1) a bitmap that sets NBITS bits per key inside ONE 32-bit word
+// (still a single L2 request per window, several times fewer false positives while the
+// bitmap is sparse) and (2) the pair table in phase 2: ONE HBM bucket per surviving window
+// answers "in A? else in B?" (quirk Q4) instead of one bucket per set.  k <= 31 only (the
+// pair table keeps its tags in the two bits a 31-mer leaves free).
+template <int NBITS>
+__device__ __forceinline__ uint32_t filter_bits(uint64_t h64)
+{
+    const uint32_t lo = (uint32_t)h64;
+    uint32_t m = 1u << (lo & 31u);
+    if (NBITS == 2) m |= 1u << ((lo >> 5) & 31u);
+    return m;
+}
+
+template <int K, int U, int NBITS>
+__global__ void __launch_bounds__(128)
+k_classify_pair(tb_batch_view b, int k_runtime, tb_pair_view P, const uint32_t *__restrict__ filter,
+                uint32_t filter_word_mask)
+{
+    const int k = K ? K : k_runtime;
+    const uint64_t kmask = (1ull << (2 * k)) - 1ull;  // k <= 31
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= b.n_tiles) return;  // warp-uniform
+    LaneCtx c;
+    lane_setup(b, tile, lane, k, c);
+    uint64_t keep_policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
+
+    // ---- phase 1 ---------------------------------------------------------------------
+    uint32_t pass = 0;
+    if (c.vmask) {
+#pragma unroll
+        for (int g = 0; g < 32; g += U) {
+            uint32_t need[U], wd[U];
+            uint32_t widx[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint64_t h64 = tb_hash64(window_key<K>(c, g + u, k, kmask));
+                need[u] = filter_bits<NBITS>(h64);
+                widx[u] = (uint32_t)(h64 >> 32) & filter_word_mask;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) wd[u] = ld_filter(filter + widx[u], 2, keep_policy);
+#pragma unroll
+            for (int u = 0; u < U; u++) pass |= ((wd[u] & need[u]) == need[u] ? 1u : 0u) << (g + u);
+        }
+        pass &= c.vmask;
+    }
+    {
+        const unsigned np = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(pass));
+        if (lane == 0 && np) atomicAdd(b.n_pass, (unsigned long long)np);
+    }
+
+    // ---- phase 2: up to four surviving windows per round, one bucket each -------------
+    uint32_t hit_a = 0, hit_b = 0;
+    uint32_t m = pass;
+    while (m) {
+        int j[4];
+        uint64_t key[4];
+        uint32_t bkt[4];
+        tb_bucket bk[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            j[q] = m ? __ffs(m) - 1 : -1;
+            if (m) m &= m - 1;
+            key[q] = window_key<0>(c, j[q] < 0 ? 0 : j[q], k, kmask);
+            bkt[q] = tb_pair_bucket_of(tb_hash64(key[q]), P.n_buckets);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (j[q] >= 0) bk[q] = tb_load_bucket(P.table + bkt[q]);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (j[q] < 0) continue;
+            uint32_t tags = tb_pair_tags(bk[q], key[q]);
+            if (!tags && tb_pair_bucket_full(bk[q])) tags = tb_pair_overflow(P, key[q], bkt[q]);
+            hit_a |= (tags & 1u) << j[q];
+            hit_b |= ((tags == 2u) ? 1u : 0u) << j[q];
+        }
+    }
+    lane_attribute(b, c, lane, hit_a, hit_b);
+}
+
+template <int NBITS>
+__global__ void __launch_bounds__(256)
+k_pair_filter_build(const unsigned long long *__restrict__ slots, uint64_t n_slots, uint32_t *filter,
+                    uint32_t filter_word_mask)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    const unsigned long long e = slots[i];
+    if (e == 0) return;
+    const uint64_t h64 = tb_hash64(e & TB_PAIR_KEYMASK);
+    atomicOr(&filter[(uint32_t)(h64 >> 32) & filter_word_mask], filter_bits<NBITS>(h64));
+}
+
 // ---- bitmap construction: one thread per table slot ---------------------------------
 __global__ void __launch_bounds__(256)
 k_filter_build(const unsigned long long *__restrict__ slots, uint64_t n_slots, uint32_t *filter,
@@ -592,6 +690,20 @@ cudaError_t launch_filtered_k(const tb_batch_view &b, int k, tb_set_view A, tb_s
     return cudaGetLastError();
 }
 
+template <int K>
+cudaError_t launch_pair_k(const tb_batch_view &b, int k, tb_pair_view P, const uint32_t *filter,
+                          uint32_t word_mask, int n_bits, cudaStream_t stream)
+{
+    const int tpb = g_tpb;
+    const int warps = tpb / 32;
+    const unsigned blocks = (unsigned)((b.n_tiles + warps - 1) / warps);
+    if (n_bits == 2)
+        k_classify_pair<K, 16, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, word_mask);
+    else
+        k_classify_pair<K, 16, 1><<<blocks, tpb, 0, stream>>>(b, k, P, filter, word_mask);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 void tb_classify_config(int unroll, int threads_per_block, int filter_unroll, int filter_mode)
@@ -654,6 +766,31 @@ cudaError_t tb_launch_classify_filtered(const tb_batch_view &b, int k, tb_set_vi
     case 31: return launch_filtered_k<31>(b, k, A, B, filter, filter_mask, stream);
     default: return launch_filtered_k<0>(b, k, A, B, filter, filter_mask, stream);
     }
+}
+
+cudaError_t tb_launch_classify_pair(const tb_batch_view &b, int k, tb_pair_view P,
+                                    const uint32_t *filter, uint32_t filter_word_mask, int n_bits,
+                                    cudaStream_t stream)
+{
+    if (b.n_tiles == 0) return cudaSuccess;
+    switch (k) {
+    case 21: return launch_pair_k<21>(b, k, P, filter, filter_word_mask, n_bits, stream);
+    case 31: return launch_pair_k<31>(b, k, P, filter, filter_word_mask, n_bits, stream);
+    default: return launch_pair_k<0>(b, k, P, filter, filter_word_mask, n_bits, stream);
+    }
+}
+
+cudaError_t tb_launch_pair_filter_build(const uint64_t *d_pair_table, uint64_t n_slots, uint32_t *filter,
+                                        uint32_t filter_word_mask, int n_bits, cudaStream_t stream)
+{
+    if (n_slots == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n_slots + 255) / 256);
+    const unsigned long long *slots = reinterpret_cast<const unsigned long long *>(d_pair_table);
+    if (n_bits == 2)
+        k_pair_filter_build<2><<<blocks, 256, 0, stream>>>(slots, n_slots, filter, filter_word_mask);
+    else
+        k_pair_filter_build<1><<<blocks, 256, 0, stream>>>(slots, n_slots, filter, filter_word_mask);
+    return cudaGetLastError();
 }
 
 cudaError_t tb_launch_filter_build(const uint64_t *d_table, uint64_t n_slots, uint32_t *filter,

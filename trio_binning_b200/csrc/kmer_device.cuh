@@ -93,6 +93,58 @@ __device__ __forceinline__ bool tb_contains(const tb_set_view &s, uint64_t key)
     return tb_probe_overflow(s, key, bucket);
 }
 
+// ---- pair table ----------------------------------------------------------------------
+// One table for BOTH sets: slot = (tags << 62) | key with tags bit 0 = "in A", bit 1 =
+// "in B" (k <= 31, so a key needs at most 62 bits); empty slot = 0.  One bucket load
+// answers "A? else B?" (quirk Q4) for a window instead of one load per set.  Buckets and
+// the multi-bit pre-filter are addressed with a 64-bit mixer.
+#define TB_PAIR_KEYMASK 0x3FFFFFFFFFFFFFFFull
+
+struct tb_pair_view {
+    const tb_bucket *table;
+    uint32_t n_buckets;
+};
+
+__host__ __device__ __forceinline__ uint64_t tb_hash64(uint64_t x)
+{
+    x *= 0x9E3779B97F4A7C15ull;
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t tb_pair_bucket_of(uint64_t h64, uint32_t n_buckets)
+{
+    return __umulhi((uint32_t)h64, n_buckets);
+}
+
+// tags of `key` in an already loaded bucket (0 = not here)
+__device__ __forceinline__ uint32_t tb_pair_tags(const tb_bucket &b, uint64_t key)
+{
+    uint32_t tags = 0;
+#pragma unroll
+    for (int i = 0; i < TB_SLOTS; i++) {
+        const uint64_t t = b.s[i] ^ key;  // same key <=> only the two tag bits differ
+        if ((t << 2) == 0) tags |= (uint32_t)(t >> 62);
+    }
+    return tags;
+}
+
+__device__ __forceinline__ bool tb_pair_bucket_full(const tb_bucket &b) { return b.s[TB_SLOTS - 1] != 0; }
+
+static __device__ __noinline__ uint32_t tb_pair_overflow(const tb_pair_view &s, uint64_t key, uint32_t bucket)
+{
+    for (uint32_t n = 1; n < s.n_buckets; n++) {
+        bucket = bucket + 1 == s.n_buckets ? 0 : bucket + 1;
+        const tb_bucket b = tb_load_bucket(s.table + bucket);
+        const uint32_t tags = tb_pair_tags(b, key);
+        if (tags) return tags;
+        if (!tb_pair_bucket_full(b)) return 0;
+    }
+    return 0;
+}
+
 // ---- base codes -----------------------------------------------------------
 // A0 C1 G2 T3 (c/kmers.c:56-68); only the four upper-case letters are bases.
 __host__ __device__ __forceinline__ bool tb_base_valid(unsigned char c)

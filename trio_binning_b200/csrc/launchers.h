@@ -16,6 +16,10 @@ cudaError_t tb_launch_insert_text(const char *d_text, uint64_t n_lines, uint64_t
 cudaError_t tb_launch_insert_keys(const uint64_t *d_keys, uint64_t n, tb_bucket *table,
                                   uint32_t n_buckets, unsigned long long *d_counters,
                                   cudaStream_t stream);
+// merge a per-set table (empty = ~0) into the pair table (empty = 0); tag 1 = A, 2 = B
+cudaError_t tb_launch_pair_insert(const uint64_t *d_src_table, uint64_t n_slots, int tag,
+                                  tb_bucket *pair_table, uint32_t n_buckets,
+                                  unsigned long long *d_counters, cudaStream_t stream);
 cudaError_t tb_launch_contains(tb_set_view set, const uint64_t *d_keys, uint64_t n,
                                unsigned char *d_out, cudaStream_t stream);
 
@@ -70,6 +74,13 @@ cudaError_t tb_launch_classify_filtered(const tb_batch_view &b, int k, tb_set_vi
                                         cudaStream_t stream);
 cudaError_t tb_launch_filter_build(const uint64_t *d_table, uint64_t n_slots, uint32_t *filter,
                                    uint32_t filter_mask, cudaStream_t stream);
+// pair-table variant: one bitmap word (n_bits = 1 or 2 bits per key) + one pair bucket per
+// surviving window; the bitmap is built from the pair table
+cudaError_t tb_launch_classify_pair(const tb_batch_view &b, int k, tb_pair_view P,
+                                    const uint32_t *filter, uint32_t filter_word_mask, int n_bits,
+                                    cudaStream_t stream);
+cudaError_t tb_launch_pair_filter_build(const uint64_t *d_pair_table, uint64_t n_slots, uint32_t *filter,
+                                        uint32_t filter_word_mask, int n_bits, cudaStream_t stream);
 cudaError_t tb_launch_fixup(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
                             cudaStream_t stream);
 cudaError_t tb_launch_finalize(const tb_batch_view &b, double scale_a, double scale_b,

@@ -102,6 +102,46 @@ k_contains(tb_set_view set, const uint64_t *__restrict__ keys, uint64_t n, unsig
     if (i < n) out[i] = tb_contains(set, keys[i]) ? 1 : 0;
 }
 
+// Merge one per-set table into the pair table: every occupied slot of `src` is inserted as
+// (tag << 62) | key; a key already present (from the other set, or a racing duplicate) just
+// gets the tag OR-ed in.
+__global__ void __launch_bounds__(256)
+k_pair_insert(const unsigned long long *__restrict__ src, uint64_t n_slots, unsigned long long tag,
+              tb_bucket *table, uint32_t n_buckets, unsigned long long *counters)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool is_new = false;
+    if (i < n_slots) {
+        const unsigned long long key = src[i];
+        if (key != TB_EMPTY) {
+            const unsigned long long entry = key | (tag << 62);
+            uint32_t bucket = tb_pair_bucket_of(tb_hash64(key), n_buckets);
+            bool done = false;
+            for (uint32_t n = 0; n < n_buckets && !done; n++) {
+                unsigned long long *slots = table[bucket].s;
+#pragma unroll
+                for (int j = 0; j < TB_SLOTS && !done; j++) {
+                    unsigned long long cur = slots[j];
+                    if (cur == 0) {
+                        cur = atomicCAS(&slots[j], 0ull, entry);
+                        if (cur == 0) {
+                            is_new = true;
+                            done = true;
+                            break;
+                        }
+                    }
+                    if (((cur ^ key) << 2) == 0) {
+                        atomicOr(&slots[j], tag << 62);
+                        done = true;
+                    }
+                }
+                bucket = bucket + 1 == n_buckets ? 0 : bucket + 1;
+            }
+        }
+    }
+    account(is_new, false, false, counters);
+}
+
 inline unsigned blocks_for(uint64_t n, unsigned tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 
 }  // namespace
@@ -123,6 +163,17 @@ cudaError_t tb_launch_insert_keys(const uint64_t *d_keys, uint64_t n, tb_bucket 
 {
     if (n == 0) return cudaSuccess;
     k_insert_keys<<<blocks_for(n, 256), 256, 0, stream>>>(d_keys, n, table, n_buckets, d_counters);
+    return cudaGetLastError();
+}
+
+cudaError_t tb_launch_pair_insert(const uint64_t *d_src_table, uint64_t n_slots, int tag,
+                                  tb_bucket *pair_table, uint32_t n_buckets,
+                                  unsigned long long *d_counters, cudaStream_t stream)
+{
+    if (n_slots == 0) return cudaSuccess;
+    k_pair_insert<<<blocks_for(n_slots, 256), 256, 0, stream>>>(
+        reinterpret_cast<const unsigned long long *>(d_src_table), n_slots, (unsigned long long)tag,
+        pair_table, n_buckets, d_counters);
     return cudaGetLastError();
 }
 

@@ -133,6 +133,7 @@ lib.tb_classifier_rerun_resident.argtypes = [C.c_void_p, C.c_int, C.c_int,
 lib.tb_classifier_rerun_resident_flush.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64,
                                                    C.POINTER(C.c_float), C.POINTER(C.c_float)]
 lib.tb_classifier_filter_passes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+lib.tb_classifier_pair_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
 lib.tb_classifier_filter_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
 lib.tb_classifier_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -541,7 +542,10 @@ class Classifier:
         """log2(bits) of the L2-resident pre-filter (0 = direct kernel) and its build time."""
         m, ms = C.c_int(), C.c_float()
         _check(lib.tb_classifier_filter_info(self._h, C.byref(m), C.byref(ms)))
-        return {"log2_bits": m.value, "build_ms": ms.value}
+        nb, nd, bits = C.c_uint32(), C.c_uint64(), C.c_int()
+        _check(lib.tb_classifier_pair_info(self._h, C.byref(nb), C.byref(nd), C.byref(bits)))
+        return {"log2_bits": m.value, "build_ms": ms.value, "pair_buckets": nb.value,
+                "pair_distinct": nd.value, "bits_per_key": bits.value if nb.value else 1}
 
     def stats(self, slot: int) -> dict:
         w, p, f, launches = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
