@@ -674,6 +674,28 @@ tb_classifier *tb_classifier_create(const hash_set *A, const hash_set *B, int64_
             return NULL;
         }
     }
+    if (c->d_filter && env_int("TB_L2_WINDOW", 0)) {
+        // experiment: pin the bitmap with the driver's persisting-L2 mechanism (set-aside +
+        // per-stream access policy window) instead of the per-load evict_last hint
+        cudaDeviceProp prop;
+        cudaGetDeviceProperties(&prop, c->device);
+        const size_t bytes = ((size_t)c->filter_mask + 1) / 8;
+        const size_t set_aside = std::min<size_t>(bytes, (size_t)prop.persistingL2CacheMaxSize);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside);
+        for (auto &s : c->slots) {
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof attr);
+            attr.accessPolicyWindow.base_ptr = c->d_filter;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)set_aside / (double)bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaError_t e = cudaStreamSetAttribute(s.stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+            if (getenv("TB_VERBOSE"))
+                fprintf(stderr, "[tb] L2 window %zu bytes, set-aside %zu: %s\n", bytes, set_aside, cudaGetErrorString(e));
+        }
+        cudaGetLastError();
+    }
     return c;
 }
 

@@ -506,7 +506,7 @@ __device__ __forceinline__ uint32_t filter_bits(uint64_t h64)
 template <int K, int U, int NBITS>
 __global__ void __launch_bounds__(128)
 k_classify_pair(tb_batch_view b, int k_runtime, tb_pair_view P, const uint32_t *__restrict__ filter,
-                uint32_t filter_word_mask)
+                uint32_t filter_word_mask, int filter_mode)
 {
     const int k = K ? K : k_runtime;
     const uint64_t kmask = (1ull << (2 * k)) - 1ull;  // k <= 31
@@ -515,8 +515,9 @@ k_classify_pair(tb_batch_view b, int k_runtime, tb_pair_view P, const uint32_t *
     if (tile >= b.n_tiles) return;  // warp-uniform
     LaneCtx c;
     lane_setup(b, tile, lane, k, c);
-    uint64_t keep_policy;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
+    uint64_t keep_policy = 0;
+    if (filter_mode == 2)
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
 
     // ---- phase 1 ---------------------------------------------------------------------
     uint32_t pass = 0;
@@ -532,7 +533,7 @@ k_classify_pair(tb_batch_view b, int k_runtime, tb_pair_view P, const uint32_t *
                 widx[u] = (uint32_t)(h64 >> 32) & filter_word_mask;
             }
 #pragma unroll
-            for (int u = 0; u < U; u++) wd[u] = ld_filter(filter + widx[u], 2, keep_policy);
+            for (int u = 0; u < U; u++) wd[u] = ld_filter(filter + widx[u], filter_mode, keep_policy);
 #pragma unroll
             for (int u = 0; u < U; u++) pass |= ((wd[u] & need[u]) == need[u] ? 1u : 0u) << (g + u);
         }
@@ -698,9 +699,9 @@ cudaError_t launch_pair_k(const tb_batch_view &b, int k, tb_pair_view P, const u
     const int warps = tpb / 32;
     const unsigned blocks = (unsigned)((b.n_tiles + warps - 1) / warps);
     if (n_bits == 2)
-        k_classify_pair<K, 16, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, word_mask);
+        k_classify_pair<K, 16, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, word_mask, g_filter_mode);
     else
-        k_classify_pair<K, 16, 1><<<blocks, tpb, 0, stream>>>(b, k, P, filter, word_mask);
+        k_classify_pair<K, 16, 1><<<blocks, tpb, 0, stream>>>(b, k, P, filter, word_mask, g_filter_mode);
     return cudaGetLastError();
 }
 
