@@ -525,3 +525,40 @@ def test_native_pipeline_equals_python_io(kmers, capsys, tmp_path):
     assert outs["native"][0].count("\n") == 600
     bins = [line.split("\t")[1] for line in outs["native"][0].splitlines()]
     assert {"A", "B", "U"} <= set(bins)
+
+
+# ---------------------------------------------------------------- the reference's own binding
+def test_reference_style_ctypes_binding(kmers):
+    """Bind the library exactly the way the reference's kmers.py does (5-field struct, the
+    four symbols, c_char_p arguments; reference kmers.py:41-93) and replay its unit tests:
+    this is the zero-edit drop-in of INTEGRATION.md section 1."""
+    from ctypes import POINTER, Structure, byref, c_char_p, c_int, c_ubyte, c_uint64, cdll
+
+    lib = cdll.LoadLibrary(kmers._lib_path)
+
+    class RefHashSet(Structure):
+        _fields_ = [("kmers", POINTER(c_uint64)), ("full", POINTER(c_ubyte)), ("hash_size", c_int),
+                    ("k", c_ubyte), ("num_kmers", c_int)]
+
+    lib.create_kmer_hash_set.argtypes = [c_char_p]
+    lib.create_kmer_hash_set.restype = POINTER(RefHashSet)
+    lib.count_kmers_in_read.argtypes = [c_char_p, POINTER(RefHashSet), POINTER(RefHashSet), POINTER(c_int), POINTER(c_int)]
+    lib.kmer_to_int.argtypes = [c_char_p, c_ubyte]
+    lib.kmer_to_int.restype = c_uint64
+    lib.reverse_complement.argtypes = [c_char_p, c_char_p, c_ubyte]
+
+    a = lib.create_kmer_hash_set(os.path.join(REF_DATA, "hapA.txt").encode("utf-8"))
+    b = lib.create_kmer_hash_set(os.path.join(REF_DATA, "hapB.txt").encode("utf-8"))
+    assert a.contents.num_kmers == 4 and b.contents.num_kmers == 3 and a.contents.k == 21
+    ca, cb = c_int(), c_int()
+    read = "CTTATCATGTCTTTGTTTTCAAAGCTTCTTAGAGGTTTTTTTTTTTGGTGTTAATTGGCATAAATTATGGCT"
+    lib.count_kmers_in_read(read.encode("utf-8"), a, b, byref(ca), byref(cb))
+    assert (ca.value, cb.value) == (2, 1)
+    assert lib.kmer_to_int(b"ATGCTAGCTAGAGAGAGAGGA", c_ubyte(21)) == 696357446508
+    out = bytes("x" * 21, "utf-8")
+    lib.reverse_complement(b"ATGCTAGCTAGAGAGAGAGGA", out, 21)
+    assert out.decode() == "TCCTCTCTCTCTAGCTAGCAT"
+    # the reference driver's arithmetic on top of it (classify_by_kmers.py:72-76, :104-115)
+    m = max(a.contents.num_kmers, b.contents.num_kmers)
+    sa, sb = 1.0 * m / a.contents.num_kmers, 1.0 * m / b.contents.num_kmers
+    assert (ca.value * sa, cb.value * sb) == (2.0, 4 / 3)
