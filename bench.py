@@ -135,6 +135,29 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Run this rank on the CPUs next to its GPU (NVML's ideal affinity) BEFORE any pinned
+    buffer is allocated, so that the staging memory is first-touched on the GPU's NUMA node:
+    with 8 ranks streaming 55 GB/s each, copies that cross the socket interconnect cap the
+    aggregate host-to-device rate."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpus = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpus + 63) // 64)
+        cpus = {i for i in range(n_cpus) if (int(words[i // 64]) >> (i % 64)) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:  # noqa: BLE001  (no NVML, no permission: stay where we are)
+        pass
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -272,6 +295,7 @@ def run_gpu_arm(args, rank, local_rank, world):
 
     if kmers.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    numa = bind_to_gpu_numa_node(local_rank)
     dist = Dist(world, "nccl")
     kmers.set_device(local_rank)
     tmp_dir = os.path.join(tempfile.gettempdir(), f"tb_bench_data_r{rank}" if world > 1 else "tb_bench_data")
@@ -486,6 +510,7 @@ def run_gpu_arm(args, rank, local_rank, world):
             "probes_per_s": probes_all / (res_ms_max / args.steps * 1e-3),
             "set_build_ms": build_ms,
             "setup_s": setup_s,
+            "cpu_affinity": f"{len(numa)} cpus next to the GPU (NVML)" if numa else "unchanged",
             "bins": {"A": int((bins == 65).sum()), "B": int((bins == 66).sum()), "U": int((bins == 85).sum())},
         }
         print(json.dumps(line), flush=True)
