@@ -347,7 +347,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     # ---- batches"): (a) packing timed on its own, (b) packed batches already in pinned
     # ---- memory -> H2D of 0.25 B/base -> kernels -> D2H, (c) ASCII in, host pack INSIDE
     # ---- the timed region, then (b)
-    host_threads = os.cpu_count() or 1
+    host_threads = len(os.sched_getaffinity(0)) or 1
     pbs = [kmers.PackedBatch(total, n_reads) for _ in range(2)]
     for pb in pbs:
         pb.pack(bases, offsets, k, threads=host_threads)

@@ -23,72 +23,40 @@ from . import kmers, seq, sharding
 DEFAULT_BATCH_BASES = 256 << 20
 
 
+# The reference's command line (classify_by_kmers.py:14-54): three positionals and four
+# options, same names, defaults and help texts; then the B200 additions.
+_REFERENCE_ARGUMENTS = (
+    (("reads",), dict(help="reads to classify into bins, in fasta/q format. Can be gzipped.")),
+    (("haplotype_a_kmers",), dict(type=kmers.create_kmer_hash_set,
+                                  help="a list of k-mers unique to haplotype A, one per line")),
+    (("haplotype_b_kmers",), dict(type=kmers.create_kmer_hash_set,
+                                  help="a list of k-mers unique to haplotype B, one per line")),
+    (("--haplotype-a-out-prefix",), dict(default="hapA", help="prefix for haplotype A output file")),
+    (("--haplotype-b-out-prefix",), dict(default="hapB", help="prefix for haplotype B output file")),
+    (("--unclassified-out-prefix",), dict(default="unclassified", help="prefix for unclassified output file")),
+    (("--no-gzip-output",), dict(action="store_true", default=False, help="don't gzip the output")),
+)
+_B200_ARGUMENTS = (
+    (("--batch-bases",), dict(type=int, default=DEFAULT_BATCH_BASES,
+                              help="bases per GPU batch (B200 addition; does not change results)")),
+    (("--python-io",), dict(action="store_true", default=False,
+                            help="read and write FASTA/FASTQ in Python like the reference instead of the "
+                                 "native multi-threaded pipeline (B200 addition; same output)")),
+    (("--gzip-level",), dict(type=int, default=9,
+                             help="compression level of the gzipped outputs; 9 is what the reference's "
+                                  "gzip.open uses (B200 addition; native pipeline only)")),
+    (("--threads",), dict(type=int, default=0,
+                          help="host threads for the native pipeline, 0 = all cores (B200 addition)")),
+)
+
+
 def parse_args(argv=None):
-    """Parse arguments (the k-mer sets are built while parsing, as in the reference)."""
-    parser = argparse.ArgumentParser(
-        description=__doc__, formatter_class=argparse.ArgumentDefaultsHelpFormatter
-    )
-    parser.add_argument(
-        "reads",
-        help="reads to classify into bins, in fasta/q format. Can be gzipped.",
-    )
-    parser.add_argument(
-        "haplotype_a_kmers",
-        type=kmers.create_kmer_hash_set,
-        help="a list of k-mers unique to haplotype A, one per line",
-    )
-    parser.add_argument(
-        "haplotype_b_kmers",
-        type=kmers.create_kmer_hash_set,
-        help="a list of k-mers unique to haplotype B, one per line",
-    )
-    parser.add_argument(
-        "--haplotype-a-out-prefix",
-        default="hapA",
-        help="prefix for haplotype A output file",
-    )
-    parser.add_argument(
-        "--haplotype-b-out-prefix",
-        default="hapB",
-        help="prefix for haplotype B output file",
-    )
-    parser.add_argument(
-        "--unclassified-out-prefix",
-        default="unclassified",
-        help="prefix for unclassified output file",
-    )
-    parser.add_argument(
-        "--no-gzip-output",
-        action="store_true",
-        help="don't gzip the output",
-        default=False,
-    )
-    parser.add_argument(
-        "--batch-bases",
-        type=int,
-        default=DEFAULT_BATCH_BASES,
-        help="bases per GPU batch (B200 addition; does not change results)",
-    )
-    parser.add_argument(
-        "--python-io",
-        action="store_true",
-        default=False,
-        help="read and write FASTA/FASTQ in Python like the reference instead of the native "
-        "multi-threaded pipeline (B200 addition; same output)",
-    )
-    parser.add_argument(
-        "--gzip-level",
-        type=int,
-        default=9,
-        help="compression level of the gzipped outputs; 9 is what the reference's gzip.open "
-        "uses (B200 addition; native pipeline only)",
-    )
-    parser.add_argument(
-        "--threads",
-        type=int,
-        default=0,
-        help="host threads for the native pipeline, 0 = all cores (B200 addition)",
-    )
+    """Parse arguments; the two k-mer sets are built on the GPU while parsing, because the
+    reference passes its set constructor as the argparse `type` of those positionals."""
+    parser = argparse.ArgumentParser(description=__doc__,
+                                     formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    for flags, options in _REFERENCE_ARGUMENTS + _B200_ARGUMENTS:
+        parser.add_argument(*flags, **options)
     return parser.parse_args(argv)
 
 

@@ -50,6 +50,19 @@ int fail(const char *fmt, ...)
                         __LINE__);                                                       \
     } while (0)
 
+// frees device memory / events when a function leaves through one of CK's early returns
+struct DeviceScratch {
+    std::vector<void *> mem;
+    std::vector<cudaEvent_t> events;
+    ~DeviceScratch()
+    {
+        for (void *p : mem)
+            if (p) cudaFree(p);
+        for (cudaEvent_t e : events)
+            if (e) cudaEventDestroy(e);
+    }
+};
+
 int env_int(const char *name, int dflt)
 {
     const char *v = getenv(name);
@@ -618,13 +631,14 @@ int tb_set_contains_keys(const hash_set *s, const uint64_t *keys, uint64_t n, un
     if (n == 0) return 0;
     uint64_t *d_keys = nullptr;
     unsigned char *d_out = nullptr;
+    DeviceScratch scratch;
     CK(cudaMalloc((void **)&d_keys, n * 8));
+    scratch.mem.push_back(d_keys);
     CK(cudaMalloc((void **)&d_out, n));
+    scratch.mem.push_back(d_out);
     CK(cudaMemcpy(d_keys, keys, n * 8, cudaMemcpyHostToDevice));
     CK(tb_launch_contains(view_of(s), d_keys, n, d_out, 0));
     CK(cudaMemcpy(out, d_out, n, cudaMemcpyDeviceToHost));
-    cudaFree(d_keys);
-    cudaFree(d_out);
     return 0;
 }
 
@@ -919,9 +933,14 @@ int tb_classifier_rerun_resident_flush(tb_classifier *c, int slot, int iters, ui
     Slot &s = c->slots[(size_t)slot];
     if (!s.has_batch || s.view.n_reads == 0) return fail("no batch resident in slot %d", slot);
     void *scratch = nullptr;
-    if (flush_bytes) CK(cudaMalloc(&scratch, flush_bytes));
+    DeviceScratch guard;
+    if (flush_bytes) {
+        CK(cudaMalloc(&scratch, flush_bytes));
+        guard.mem.push_back(scratch);
+    }
     // four events per iteration: step begin/end and classify begin/end
-    std::vector<cudaEvent_t> ev((size_t)iters * 4);
+    std::vector<cudaEvent_t> &ev = guard.events;
+    ev.assign((size_t)iters * 4, nullptr);
     for (auto &e : ev) CK(cudaEventCreate(&e));
     CK(cudaStreamSynchronize(s.stream));
     for (int i = 0; i < iters; i++) {
@@ -940,8 +959,6 @@ int tb_classifier_rerun_resident_flush(tb_classifier *c, int slot, int iters, ui
         CK(cudaEventElapsedTime(&t, ev[(size_t)4 * i + 1], ev[(size_t)4 * i + 2]));
         cls += t;
     }
-    for (auto &e : ev) cudaEventDestroy(e);
-    if (scratch) cudaFree(scratch);
     if (ms_total) *ms_total = total;
     if (ms_classify) *ms_classify = cls;
     return 0;
