@@ -347,7 +347,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     # ---- batches"): (a) packing timed on its own, (b) packed batches already in pinned
     # ---- memory -> H2D of 0.25 B/base -> kernels -> D2H, (c) ASCII in, host pack INSIDE
     # ---- the timed region, then (b)
-    host_threads = len(os.sched_getaffinity(0)) or 1
+    host_threads = max(1, (len(os.sched_getaffinity(0)) or 1) // world)  # ranks share the host cores
     pbs = [kmers.PackedBatch(total, n_reads) for _ in range(2)]
     for pb in pbs:
         pb.pack(bases, offsets, k, threads=host_threads)
@@ -371,6 +371,26 @@ def run_gpu_arm(args, rank, local_rank, world):
         clf.wait(1)
         return max(clf.elapsed_ms(0, 0, 0, 1), clf.elapsed_ms(0, 0, 1, 1))
 
+    def hybrid_pass(n_steps):
+        """ASCII in both cases: even steps send the ASCII batch (PCIe does the work, device
+        packs), odd steps pack on the host cores and send 0.25 B/base -- the two resources
+        (PCIe link, host cores) work in parallel on alternating slots."""
+        clf.mark(0, 0)
+        for i in range(n_steps):
+            slot = i & 1
+            if i >= 2:
+                clf.wait(slot)
+            if slot == 0:
+                clf.submit(0, None, None, n_reads=n_reads)
+            else:
+                pbs[1].pack(bases, offsets, k, threads=host_threads)
+                clf.submit_packed(1, pbs[1])
+        clf.mark(0, 1)
+        clf.mark(1, 1)
+        clf.wait(0)
+        clf.wait(1)
+        return max(clf.elapsed_ms(0, 0, 0, 1), clf.elapsed_ms(0, 0, 1, 1))
+
     packed_pass(3, False)
     pca, pcb, *_ = clf.result(0)
     assert (pca == ca).all() and (pcb == cb).all(), "host-packed path differs from the ASCII path"
@@ -378,6 +398,10 @@ def run_gpu_arm(args, rank, local_rank, world):
     e2e_packed_ms = dist.reduce(packed_pass(args.steps, False), "MAX")
     dist.barrier()
     e2e_hostpack_ms = dist.reduce(packed_pass(max(3, args.steps // 5), True), "MAX") * args.steps / max(3, args.steps // 5)
+    hybrid_pass(4)
+    dist.barrier()
+    n_hyb = max(4, (args.steps // 2) & ~1)
+    e2e_hybrid_ms = dist.reduce(hybrid_pass(n_hyb), "MAX") * args.steps / n_hyb
     # leave an ASCII batch resident in slot 0 for the device-only timing below
     clf.submit(0, None, None, n_reads=n_reads)
     clf.wait(0)
@@ -480,26 +504,43 @@ def run_gpu_arm(args, rank, local_rank, world):
             for r in range(0, sample_reads, max(1, sample_reads // 25)):
                 got = lib.count(bytes(bases[offsets[r]:offsets[r + 1]]), _REF["A"], _REF["B"])
                 assert got == (ca[r], cb[r]), f"parity failure on read {r}: cpu {got} gpu {(ca[r], cb[r])}"
+        d2h = n_reads * (4 + 4 + 8 + 8 + 1)
+        ascii_h2d = total + 8 * (n_reads + 1)
+        e2e_variants = {
+            "ascii_device_pack": {
+                "value": total_all / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": ascii_h2d, "d2h_bytes_per_step": d2h,
+                "api": "tb_classifier_submit/wait (C ABI): ASCII reads in pinned host memory -> H2D 1 B/base -> "
+                       "k_pack on the device -> classify -> D2H; 2 slots in flight"},
+            "ascii_host_pack": {
+                "value": total_all / (e2e_hostpack_ms / args.steps * 1e-3), "unit": UNIT,
+                "ms_per_step": e2e_hostpack_ms / args.steps,
+                "h2d_bytes_per_step": pbs[0].h2d_bytes, "d2h_bytes_per_step": d2h,
+                "api": f"ASCII reads in pinned host memory -> tb_pack_reads on {host_threads} host threads INSIDE the "
+                       "timed region -> tb_classifier_submit_packed (H2D 0.25 B/base) -> classify -> D2H"},
+            "ascii_hybrid": {
+                "value": total_all / (e2e_hybrid_ms / args.steps * 1e-3), "unit": UNIT,
+                "ms_per_step": e2e_hybrid_ms / args.steps,
+                "h2d_bytes_per_step": (ascii_h2d + pbs[0].h2d_bytes) // 2, "d2h_bytes_per_step": d2h,
+                "api": "ASCII reads in pinned host memory; slot 0 takes the ASCII route (tb_classifier_submit), slot 1 "
+                       f"the host-pack route (tb_pack_reads on {host_threads} threads + tb_classifier_submit_packed), "
+                       "alternating, both inside the timed region: PCIe link and host cores work in parallel"},
+        }
+        best = max(e2e_variants, key=lambda name: e2e_variants[name]["value"])
+        e2e_best = dict(e2e_variants[best], route=best)
         line = {
             "metric": METRIC, "value": total_all / (res_ms_max / args.steps * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": res_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": workload_config(args, wl),
-            "e2e": {"value": total_all / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": total + 8 * (n_reads + 1),
-                    "d2h_bytes_per_step": n_reads * (4 + 4 + 8 + 8 + 1),
-                    "ms_per_step": e2e_ms / args.steps,
-                    "api": "tb_classifier_submit/wait (C ABI), pinned host buffers, 2 slots in flight"},
+            "e2e": e2e_best,
+            "e2e_variants": e2e_variants,
             "e2e_packed": {"value": total_all / (e2e_packed_ms / args.steps * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": pbs[0].h2d_bytes, "d2h_bytes_per_step": n_reads * (4 + 4 + 8 + 8 + 1),
                            "ms_per_step": e2e_packed_ms / args.steps,
                            "api": "tb_classifier_submit_packed: 2-bit batches packed by tb_pack_reads, already in "
                                   "pinned host memory when the timed region starts (packing is reported in host_pack)"},
-            "e2e_ascii_hostpack": {"value": total_all / (e2e_hostpack_ms / args.steps * 1e-3), "unit": UNIT,
-                                   "ms_per_step": e2e_hostpack_ms / args.steps,
-                                   "api": "ASCII in pinned host memory -> tb_pack_reads on the host cores inside the "
-                                          "timed region -> tb_classifier_submit_packed"},
             "host_pack": {"value": total / pack_s, "unit": UNIT, "threads": host_threads,
                           "what": "tb_pack_reads (AVX2, multi-threaded): ASCII -> 2-bit pinned batch, this rank"},
             "gpu_launches": 5 * args.steps,

@@ -12,6 +12,7 @@
 //           leading windows to replay literally + the ASCII prefix the replay needs
 // No k-mer lookups happen here; this is format conversion only.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -75,6 +76,37 @@ __attribute__((target("avx2"))) inline void pack32_avx2(const unsigned char *p, 
 }
 #endif
 
+// 64 ASCII bytes -> two 64-bit words + 64-bit validity mask (AVX-512 F+BW)
+__attribute__((target("avx512f,avx512bw"))) inline void pack64_avx512(const unsigned char *p, uint64_t &f0,
+                                                                      uint64_t &f1, uint64_t &valid)
+{
+    const __m512i x = _mm512_loadu_si512((const void *)p);
+    const __mmask64 ok = _mm512_cmpeq_epi8_mask(x, _mm512_set1_epi8('A')) |
+                         _mm512_cmpeq_epi8_mask(x, _mm512_set1_epi8('C')) |
+                         _mm512_cmpeq_epi8_mask(x, _mm512_set1_epi8('G')) |
+                         _mm512_cmpeq_epi8_mask(x, _mm512_set1_epi8('T'));
+    valid = (uint64_t)ok;
+    __m512i code = _mm512_xor_si512(_mm512_srli_epi16(x, 1), _mm512_srli_epi16(x, 2));
+    code = _mm512_maskz_and_epi64(0xFF, code, _mm512_set1_epi8(3));
+    code = _mm512_maskz_mov_epi8(ok, code);
+    const __m512i nib = _mm512_maddubs_epi16(code, _mm512_set1_epi16(0x0401));
+    const __m512i byt = _mm512_madd_epi16(nib, _mm512_set1_epi32(0x00100001));
+    const __m128i out = _mm512_cvtepi32_epi8(byt);  // 16 dwords -> 16 bytes = 64 bases
+    f0 = (uint64_t)_mm_extract_epi64(out, 0);
+    f1 = (uint64_t)_mm_extract_epi64(out, 1);
+}
+
+bool have_avx512()
+{
+#if defined(__x86_64__)
+    static const bool v = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+                          !getenv("TB_NO_AVX512");
+    return v;
+#else
+    return false;
+#endif
+}
+
 bool have_avx2()
 {
 #if defined(__x86_64__)
@@ -111,10 +143,26 @@ void pack_range(const unsigned char *ascii, int64_t total, const int64_t *offset
                 std::vector<DirtyWord> &dirty_out, std::vector<int64_t> &ub_reads)
 {
     const bool avx2 = have_avx2();
+#if defined(__x86_64__)
+    const bool avx512 = have_avx512();
+#endif
     for (int64_t w = w0; w < w1; w++) {
         const int64_t p0 = w * 32;
         uint64_t f;
         uint32_t valid;
+#if defined(__x86_64__)
+        if (avx512 && w + 1 < w1 && p0 + 64 <= total) {
+            // common case: two clean words at once
+            uint64_t fa, fb, v64;
+            pack64_avx512(ascii + p0, fa, fb, v64);
+            if (v64 == ~0ull) {
+                F[w] = fa;
+                F[w + 1] = fb;
+                w++;
+                continue;
+            }
+        }
+#endif
         if (p0 + 32 <= total) {
 #if defined(__x86_64__)
             if (avx2)
