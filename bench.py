@@ -449,11 +449,15 @@ def run_gpu_arm(args, rank, local_rank, world):
             achieved = algo_bytes / cls_s / 1e9
             roofline = {
                 "bound": "l2",
-                "kernel": f"k_classify_pair<{k},16,{finfo['bits_per_key']}>" if pair else f"k_classify_filtered<{k},16>",
-                "note": "the bitmap pre-filter (2^%d bits, %d bit(s) per key, L2-resident, evict_last) answers %.2f%% of "
-                        "the windows without touching HBM; survivors read %s; the kernel is bound by L2 sector "
-                        "requests (1 per SM per clock), not by HBM -- see hbm{} for the HBM side"
-                        % (finfo["log2_bits"], finfo["bits_per_key"], 100.0 * (1 - passes / max(1, windows)),
+                "kernel": (f"k_classify_pair_mini<{k},8,{finfo['bits_per_key']}>" if finfo.get("minimizer") else
+                           f"k_classify_pair<{k},16,{finfo['bits_per_key']}>") if pair else f"k_classify_filtered<{k},16>",
+                "note": "the bitmap pre-filter (2^%d bits, %d bit(s) per key, %s, evict_last) answers %.2f%% of "
+                        "the windows without touching the tables; survivors read %s; the kernel is bound by L1/L2 "
+                        "sector requests (1 per SM per clock), not by HBM -- see hbm{} for the HBM side"
+                        % (finfo["log2_bits"], finfo["bits_per_key"],
+                           "sectors addressed by the k-mers' minimizers so that consecutive windows re-use them from L1"
+                           if finfo.get("minimizer") else "L2-resident",
+                           100.0 * (1 - passes / max(1, windows)),
                            "one bucket of the tagged A+B pair table" if pair else "one bucket of A and one of B"),
                 "achieved": achieved,
                 "peak": (ceil_l2 * 32 / 1e9) if ceil_l2 else None,

@@ -227,6 +227,9 @@ int tb_classifier_filter_info(tb_classifier *c, int *log2_bits, float *build_ms)
 /* The classifier's pair table (one tagged table for both sets, k <= 31; TB_PAIR=0 turns it
  * off): buckets (0 = none), distinct keys of A u B, bitmap bits set per key. */
 int tb_classifier_pair_info(tb_classifier *c, uint32_t *n_buckets, uint64_t *n_distinct, int *filter_bits);
+/* 1 if the classifier's bitmap sectors are addressed by the keys' minimizers (the mode for
+ * sets too large for an L2-resident bitmap; TB_MINIMIZER=0|1 forces it). */
+int tb_classifier_minimizer_mode(tb_classifier *c);
 /* Counters of the last batch in a slot: windows, probes as the reference performs
  * them (W + (W - hits_A)), reads that took the Q3-UB fix-up path. */
 int tb_classifier_stats(tb_classifier *c, int slot, uint64_t *n_windows,

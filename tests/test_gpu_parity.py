@@ -392,7 +392,7 @@ def test_config2_full_size_properties(kmers, oracle, tmp_path_factory):
 
 
 # ---------------------------------------------------------------- pre-filter on / off
-@pytest.mark.parametrize("k", [21, 32, 9])
+@pytest.mark.parametrize("k", [21, 31, 32, 9])
 def test_prefilter_does_not_change_results(kmers, oracle, k):
     """The L2-resident bitmap in front of the exact tables may only skip work: direct
     kernel (TB_FILTER_LOG2=0), a saturated 1-kbit bitmap (everything passes), a sparse one
@@ -408,10 +408,10 @@ def test_prefilter_does_not_change_results(kmers, oracle, k):
     oa, ob = oracle.set_from_ints(ka, k), oracle.set_from_ints(kb, k)
     wa, wb = oracle.count_batch(bases, offsets, oa, ob)
     seen, pair_seen = set(), set()
-    saved = {v: os.environ.get(v) for v in ("TB_FILTER_LOG2", "TB_PAIR", "TB_FILTER_BITS")}
+    saved = {v: os.environ.get(v) for v in ("TB_FILTER_LOG2", "TB_PAIR", "TB_FILTER_BITS", "TB_MINIMIZER")}
     try:
-        for pair, bits in (("0", "1"), ("1", "1"), ("1", "2")):
-            os.environ["TB_PAIR"], os.environ["TB_FILTER_BITS"] = pair, bits
+        for pair, bits, mini in (("0", "1", "0"), ("1", "1", "0"), ("1", "2", "0"), ("1", "2", "1"), ("1", "1", "1")):
+            os.environ["TB_PAIR"], os.environ["TB_FILTER_BITS"], os.environ["TB_MINIMIZER"] = pair, bits, mini
             for setting in ("0", "10", "20", "26", None):
                 if setting is None:
                     os.environ.pop("TB_FILTER_LOG2", None)
@@ -423,7 +423,9 @@ def test_prefilter_does_not_change_results(kmers, oracle, k):
                     pair_seen.add((info["pair_buckets"] > 0, info["bits_per_key"]))
                     clf.submit(0, bases, offsets)
                     ca, cb, *_ = clf.result(0)
-                    assert (ca == wa).all() and (cb == wb).all(), (pair, bits, setting)
+                    assert (ca == wa).all() and (cb == wb).all(), (pair, bits, mini, setting)
+                    if k <= 31 and pair == "1" and setting != "0":
+                        assert info["minimizer"] == (mini == "1")
     finally:
         for v, val in saved.items():
             if val is None:

@@ -30,7 +30,7 @@ st = clf.stats(0)
 clf.rerun_resident(0, 3)
 ms, cls = clf.rerun_resident(0, 5)
 fi = clf.filter_info()
-print(f"filter=2^{fi['log2_bits']} pair={int(fi['pair_buckets']>0)} bits={fi['bits_per_key']} passes={clf.filter_passes(0)/max(1,st['windows']):.4f} FU={os.environ.get('TB_FILTER_UNROLL','16')} keys={n_keys} lf={lf} buckets={A.contents.n_buckets} table_MB={A.contents.n_buckets*32/1e6:.0f}x2 "
+print(f"filter=2^{fi['log2_bits']} pair={int(fi['pair_buckets']>0)} mini={int(fi['minimizer'])} bits={fi['bits_per_key']} passes={clf.filter_passes(0)/max(1,st['windows']):.4f} FU={os.environ.get('TB_FILTER_UNROLL','16')} keys={n_keys} lf={lf} buckets={A.contents.n_buckets} table_MB={A.contents.n_buckets*32/1e6:.0f}x2 "
       f"reads={n_reads}x{mean_len} k={k} UNROLL={os.environ.get('TB_UNROLL','8')} TPB={os.environ.get('TB_TPB','128')} "
       f"L2G={os.environ.get('TB_L2_FETCH_GRANULARITY','32')}: step {ms/5:.3f} ms, classify {cls/5:.3f} ms, "
       f"{total/(cls/5*1e-3)/1e9:.2f} Gbases/s, {st['probes']/(cls/5*1e-3)/1e9:.2f} Gprobes/s "

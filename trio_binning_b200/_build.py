@@ -45,7 +45,8 @@ def needs_build():
 def build(force=False, verbose=False, extra_flags=()):
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags) + [os.path.join(CSRC, f) for f in SOURCES]
+    extra_env = os.environ.get("TB_NVCC_EXTRA", "").split()  # e.g. -DTB_MINI_MIN_BLOCKS=6 (tuning experiments)
+    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags) + extra_env + [os.path.join(CSRC, f) for f in SOURCES]
     cmd += ["-o", LIB_PATH]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)

@@ -102,7 +102,7 @@ int use_device(int device)
             }
         }
         cudaGetLastError();
-        tb_classify_config(env_int("TB_UNROLL", 4), env_int("TB_TPB", 128), env_int("TB_FILTER_UNROLL", 16),
+        tb_classify_config(env_int("TB_UNROLL", 4), env_int("TB_TPB", 128), env_int("TB_FILTER_UNROLL", 8),
                             env_int("TB_FILTER_MODE", 2));
         g_device_ready[device] = true;
     }
@@ -329,6 +329,8 @@ struct tb_classifier {
     uint32_t pair_buckets = 0;
     uint64_t pair_distinct = 0;
     int filter_bits = 1;
+    uint32_t filter_word_mask = 0;  // (bits / 32) - 1
+    bool mini = false;              // bitmap sectors addressed by the key's minimizer
 };
 
 namespace {
@@ -396,9 +398,12 @@ int enqueue_kernels(tb_classifier *c, Slot &s, cudaEvent_t before_classify, cuda
     CK(tb_launch_pack(s.view, c->k, s.stream));
     CK(tb_launch_index(s.view, c->k, s.stream));
     if (before_classify) CK(cudaEventRecord(before_classify, s.stream));
-    if (c->d_pair && c->d_filter) {
+    if (c->d_pair && c->d_filter && c->mini) {
         tb_pair_view P = { c->d_pair, c->pair_buckets };
-        CK(tb_launch_classify_pair(s.view, c->k, P, c->d_filter, c->filter_mask >> 5, c->filter_bits, s.stream));
+        CK(tb_launch_classify_pair_mini(s.view, c->k, P, c->d_filter, c->filter_word_mask >> 3, c->filter_bits, s.stream));
+    } else if (c->d_pair && c->d_filter) {
+        tb_pair_view P = { c->d_pair, c->pair_buckets };
+        CK(tb_launch_classify_pair(s.view, c->k, P, c->d_filter, c->filter_word_mask, c->filter_bits, s.stream));
     } else if (c->d_filter)
         CK(tb_launch_classify_filtered(s.view, c->k, A, B, c->d_filter, c->filter_mask, s.stream));
     else
@@ -417,28 +422,38 @@ int build_filter(tb_classifier *c)
 {
     int m = env_int("TB_FILTER_LOG2", -1);
     if (m == 0) return 0;
+    const bool pair_ok = c->k <= 31 && env_int("TB_PAIR", 1) != 0;
+    // minimizer-addressed sectors (default whenever the pair table exists): consecutive windows
+    // share bitmap sectors, so the bitmap may be far larger than L2 and still cheap to read
+    c->mini = pair_ok && env_int("TB_MINIMIZER", 1) != 0;
     if (m < 0) {
-        // >= 16 bits per key up to 2^29 bits (64 MB: what stays L2-resident next to the
-        // table traffic); very large sets do better with 2^30 although it spills
-        // (profiles/r1_kernel_variants_filtered.txt).
         const uint64_t n = c->A->n_distinct + c->B->n_distinct;
-        m = 16;
-        while (m < 29 && (1ull << m) < 16 * n) m++;
-        if (n >= (1ull << 27)) m = 30;
+        if (c->mini) {
+            // >= 16 bits per key, 2^16 .. 2^35 bits (4 GB): C2 2^29, C3 2^33, C4 2^34
+            m = 16;
+            while (m < 35 && (1ull << m) < 16 * n) m++;
+        } else {
+            // hash-addressed words: keep the bitmap L2-resident (<= 2^29 bits = 64 MB); very
+            // large sets do better with 2^30 although it spills
+            m = 16;
+            while (m < 29 && (1ull << m) < 16 * n) m++;
+            if (n >= (1ull << 27)) m = 30;
+        }
     }
     if (m < 10) m = 10;
-    if (m > 32) m = 32;
+    if (m > (c->mini ? 35 : 32)) m = c->mini ? 35 : 32;
     const uint64_t bits = 1ull << m;
     CK(cudaMalloc((void **)&c->d_filter, bits / 8));
     CK(cudaMemset(c->d_filter, 0, bits / 8));
-    c->filter_mask = (uint32_t)(bits - 1);
+    c->filter_mask = (uint32_t)(bits - 1);  // only used by the two-table kernel (m <= 32)
+    c->filter_word_mask = (uint32_t)((bits >> 5) - 1);
     c->filter_log2 = m;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, 0));
     const uint64_t slots_a = (uint64_t)c->A->n_buckets * TB_SLOTS, slots_b = (uint64_t)c->B->n_buckets * TB_SLOTS;
-    if (c->k <= 31 && env_int("TB_PAIR", 1) != 0) {
+    if (pair_ok) {
         // one tagged table for both sets
         const uint64_t n = c->A->n_distinct + c->B->n_distinct;
         const uint64_t nb = (uint64_t)((double)n / (TB_SLOTS * g_load_factor)) + 1;
@@ -457,8 +472,12 @@ int build_filter(tb_classifier *c)
         int nbits = env_int("TB_FILTER_BITS", 0);
         if (nbits != 1 && nbits != 2) nbits = ((double)n / (double)bits < 0.4) ? 2 : 1;
         c->filter_bits = nbits;
-        CK(tb_launch_pair_filter_build(reinterpret_cast<const uint64_t *>(c->d_pair), nb * TB_SLOTS,
-                                       c->d_filter, c->filter_mask >> 5, nbits, 0));
+        if (c->mini)
+            CK(tb_launch_pair_filter_build_mini(reinterpret_cast<const uint64_t *>(c->d_pair), nb * TB_SLOTS,
+                                                c->d_filter, c->filter_word_mask >> 3, nbits, c->k, 0));
+        else
+            CK(tb_launch_pair_filter_build(reinterpret_cast<const uint64_t *>(c->d_pair), nb * TB_SLOTS,
+                                           c->d_filter, c->filter_word_mask, nbits, 0));
     } else {
         CK(tb_launch_filter_build(c->A->d_table, slots_a, c->d_filter, c->filter_mask, 0));
         CK(tb_launch_filter_build(c->B->d_table, slots_b, c->d_filter, c->filter_mask, 0));
@@ -867,9 +886,12 @@ int tb_classifier_submit_packed(tb_classifier *c, int slot, const tb_packed_batc
     const tb_set_view A = view_of(c->A), B = view_of(c->B);
     CK(tb_launch_index_packed(v, s.d_dirty_idx, s.d_e_words, pb->n_dirty, s.d_ub_read, s.d_ub_skip,
                               pb->n_ub, st));
-    if (c->d_pair && c->d_filter) {
+    if (c->d_pair && c->d_filter && c->mini) {
         tb_pair_view P = { c->d_pair, c->pair_buckets };
-        CK(tb_launch_classify_pair(v, c->k, P, c->d_filter, c->filter_mask >> 5, c->filter_bits, st));
+        CK(tb_launch_classify_pair_mini(v, c->k, P, c->d_filter, c->filter_word_mask >> 3, c->filter_bits, st));
+    } else if (c->d_pair && c->d_filter) {
+        tb_pair_view P = { c->d_pair, c->pair_buckets };
+        CK(tb_launch_classify_pair(v, c->k, P, c->d_filter, c->filter_word_mask, c->filter_bits, st));
     } else if (c->d_filter)
         CK(tb_launch_classify_filtered(v, c->k, A, B, c->d_filter, c->filter_mask, st));
     else
@@ -1002,6 +1024,11 @@ int tb_classifier_stats(tb_classifier *c, int slot, uint64_t *n_windows, uint64_
     }
     if (n_kernel_launches) *n_kernel_launches = s.view.n_reads ? 5 : 0;
     return 0;
+}
+
+int tb_classifier_minimizer_mode(tb_classifier *c)
+{
+    return c && c->mini ? 1 : 0;
 }
 
 int tb_classifier_pair_info(tb_classifier *c, uint32_t *n_buckets, uint64_t *n_distinct, int *filter_bits)

@@ -227,6 +227,7 @@ struct LaneCtx {
     int64_t r, end;       // read containing p0 and its end offset
     uint32_t vmask;       // bit j: window j lies inside one read and is not left to k_fixup
     bool fast;            // all 32 windows valid and in read r
+    bool clean;           // neither word of the span holds a non-ACGT base (E == F)
 };
 
 template <int K>
@@ -250,6 +251,7 @@ __device__ __forceinline__ void lane_setup(const tb_batch_view &b, int64_t tile,
     const bool d1 = lane < 31 ? (d >> (lane + 1)) & 1u : dn & 1u;
     const uint64_t e0 = d0 ? b.E[w] : c.f0;
     const uint64_t e1 = d1 ? b.E[w + 1] : c.f1;
+    c.clean = !(d0 | d1);
     // reverse complement of the span: base s of the span sits at base 63-s
     c.r_lo = tb_revcomp64(e1);
     c.r_hi = tb_revcomp64(e0);
@@ -587,6 +589,199 @@ k_pair_filter_build(const unsigned long long *__restrict__ slots, uint64_t n_slo
     atomicOr(&filter[(uint32_t)(h64 >> 32) & filter_word_mask], filter_bits<NBITS>(h64));
 }
 
+// ---- minimizer-addressed bitmap (large sets) ----------------------------------------------
+// When A u B is so large that no selective bitmap fits in L2, what limits the kernel is HBM
+// again: one bitmap sector miss per window.  Consecutive windows of a read overlap in k-1
+// bases, so they usually share their MINIMIZER (the canonical m-mer with the smallest hash
+// among the w = k-m+1 m-mers of the k-mer).  Here the 32-byte bitmap SECTOR of a key is chosen
+// by its minimizer and only the word/bits inside the sector by the k-mer itself: a lane that
+// walks 32 consecutive windows then touches a new sector only every (w+1)/2 windows on
+// average and finds the others in L1 -- 3-4x fewer L2 requests and HBM sector fetches, which
+// also makes bitmaps far beyond the L2 size (2^31..2^33 bits) affordable.  m is large enough
+// (15/16) that many minimizer values share a sector, which evens out the skew of minimizer
+// popularity.  The minimizer is a pure function of the key VALUE, so stored keys (raw, Q1)
+// and looked-up keys agree whatever strand or scratch quirk produced them.
+__host__ __device__ __forceinline__ int tb_minimizer_m(int k) { return k >= 22 ? 16 : (k >= 7 ? k - 6 : 1); }
+
+__device__ __forceinline__ uint32_t mmer_mix(uint32_t c)
+{
+    c *= 0x9E3779B1u;
+    c ^= c >> 15;
+    c *= 0x85EBCA77u;
+    c ^= c >> 13;
+    return c;
+}
+
+// reverse complement of an m-mer held in the low 2m bits
+__device__ __forceinline__ uint32_t mmer_revcomp(uint32_t f, int m)
+{
+    uint32_t x = __brev(~f);
+    x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+    return x >> (32 - 2 * m);
+}
+
+// smallest hash over the canonical m-mers of a k-mer given as its integer key
+__device__ __forceinline__ uint32_t minimizer_of_key(uint64_t key, int k, int m)
+{
+    const uint32_t mmask = m == 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+    uint32_t best = 0xFFFFFFFFu;
+    for (int i = 0; i + m <= k; i++) {
+        const uint32_t f = (uint32_t)(key >> (2 * i)) & mmask;
+        const uint32_t r = mmer_revcomp(f, m);
+        const uint32_t h = mmer_mix(f < r ? f : r);
+        best = h < best ? h : best;
+    }
+    return best;
+}
+
+// 13 well-mixed bits of the key are all phase 1 needs (word in the sector + bit positions):
+// a two-multiply 32-bit mixer instead of the 64-bit one (the pair bucket is only computed
+// for the few survivors, in phase 2)
+__device__ __forceinline__ uint32_t filter_hash32(uint64_t key)
+{
+    uint32_t x = (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA77u;
+    x ^= x >> 15;
+    x *= 0x2C1B3C6Du;
+    x ^= x >> 13;
+    return x;
+}
+
+// word index of a key's bitmap word: sector from the minimizer, word in the sector from the k-mer
+__device__ __forceinline__ uint32_t mini_word_index(uint32_t min_hash, uint32_t fh, uint32_t sector_mask)
+{
+    uint32_t s = min_hash * 0xC2B2AE35u;  // the minimum of several hashes is biased small: re-spread
+    s ^= s >> 16;
+    return ((s & sector_mask) << 3) | ((fh >> 10) & 7u);
+}
+
+__device__ __forceinline__ uint32_t ld_filter_l1(const uint32_t *p, uint64_t policy)
+{
+    uint32_t v;  // allocate in L1 (the next windows re-read this sector), keep in L2
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+    return v;
+}
+
+#ifndef TB_MINI_MIN_BLOCKS
+#define TB_MINI_MIN_BLOCKS 6
+#endif
+template <int K, int U, int NBITS>
+__global__ void __launch_bounds__(128, TB_MINI_MIN_BLOCKS)
+k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint32_t *__restrict__ filter,
+                     uint32_t sector_mask)
+{
+    const int k = K ? K : k_runtime;
+    const int m = tb_minimizer_m(k);
+    constexpr int MC = K ? (K >= 22 ? 16 : K - 6) : 1;   // compile-time m for the unrolled path
+    constexpr int WC = K ? K - MC + 1 : 1;               // m-mers per k-mer
+    const uint64_t kmask = (1ull << (2 * k)) - 1ull;  // k <= 31
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= b.n_tiles) return;  // warp-uniform
+    LaneCtx c;
+    lane_setup(b, tile, lane, k, c);
+    uint64_t keep_policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
+
+    uint32_t pass = 0;
+    if (c.vmask) {
+        if (K != 0 && c.clean) {
+            // ---- all bases valid: m-mer hashes straight from the two streams, sliding minimum
+            constexpr uint32_t MMASK = MC == 16 ? 0xFFFFFFFFu : ((1u << (2 * MC)) - 1u);
+            uint32_t hm[32 + WC];
+#pragma unroll
+            for (int q = 0; q < WC - 1; q++) {
+                const uint32_t f = (uint32_t)extract128(c.f0, c.f1, 2 * q) & MMASK;
+                const uint32_t r = (uint32_t)extract128(c.r_lo, c.r_hi, 2 * (64 - q - MC)) & MMASK;
+                hm[q] = mmer_mix(f < r ? f : r);
+            }
+#pragma unroll
+            for (int g = 0; g < 32; g += U) {
+                uint32_t need[U], wd[U], widx[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int j = g + u, q = j + WC - 1;
+                    {
+                        const uint32_t f = (uint32_t)extract128(c.f0, c.f1, 2 * q) & MMASK;
+                        const uint32_t r = (uint32_t)extract128(c.r_lo, c.r_hi, 2 * (64 - q - MC)) & MMASK;
+                        hm[q] = mmer_mix(f < r ? f : r);
+                    }
+                    uint32_t mn = hm[j];
+#pragma unroll
+                    for (int t = 1; t + 1 < WC; t += 2) mn = __vimin3_u32(mn, hm[j + t], hm[j + t + 1]);
+                    if ((WC & 1) == 0) mn = min(mn, hm[j + WC - 1]);
+                    const uint32_t fh = filter_hash32(window_key<K>(c, j, k, kmask));
+                    need[u] = filter_bits<NBITS>(fh);
+                    widx[u] = mini_word_index(mn, fh, sector_mask);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) wd[u] = ld_filter_l1(filter + widx[u], keep_policy);
+#pragma unroll
+                for (int u = 0; u < U; u++) pass |= ((wd[u] & need[u]) == need[u] ? 1u : 0u) << (g + u);
+            }
+        } else {
+            // ---- a non-ACGT base nearby (or an unusual k): minimizer from the key itself
+            for (int j = 0; j < 32; j++) {
+                if (!((c.vmask >> j) & 1u)) continue;
+                const uint64_t key = window_key<0>(c, j, k, kmask);
+                const uint32_t fh = filter_hash32(key);
+                const uint32_t need = filter_bits<NBITS>(fh);
+                const uint32_t wd = ld_filter_l1(filter + mini_word_index(minimizer_of_key(key, k, m), fh, sector_mask),
+                                                 keep_policy);
+                pass |= ((wd & need) == need ? 1u : 0u) << j;
+            }
+        }
+        pass &= c.vmask;
+    }
+    {
+        const unsigned np = __reduce_add_sync(0xFFFFFFFFu, (unsigned)__popc(pass));
+        if (lane == 0 && np) atomicAdd(b.n_pass, (unsigned long long)np);
+    }
+
+    // ---- phase 2 (as in k_classify_pair) ------------------------------------------------
+    uint32_t hit_a = 0, hit_b = 0;
+    uint32_t mm = pass;
+    while (mm) {
+        int j[4];
+        uint64_t key[4];
+        uint32_t bkt[4];
+        tb_bucket bk[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            j[q] = mm ? __ffs(mm) - 1 : -1;
+            if (mm) mm &= mm - 1;
+            key[q] = window_key<0>(c, j[q] < 0 ? 0 : j[q], k, kmask);
+            bkt[q] = tb_pair_bucket_of(tb_hash64(key[q]), P.n_buckets);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (j[q] >= 0) bk[q] = tb_load_bucket(P.table + bkt[q]);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (j[q] < 0) continue;
+            uint32_t tags = tb_pair_tags(bk[q], key[q]);
+            if (!tags && tb_pair_bucket_full(bk[q])) tags = tb_pair_overflow(P, key[q], bkt[q]);
+            hit_a |= (tags & 1u) << j[q];
+            hit_b |= ((tags == 2u) ? 1u : 0u) << j[q];
+        }
+    }
+    lane_attribute(b, c, lane, hit_a, hit_b);
+}
+
+template <int NBITS>
+__global__ void __launch_bounds__(256)
+k_pair_filter_build_mini(const unsigned long long *__restrict__ slots, uint64_t n_slots, uint32_t *filter,
+                         uint32_t sector_mask, int k)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    const unsigned long long e = slots[i];
+    if (e == 0) return;
+    const uint64_t key = e & TB_PAIR_KEYMASK;
+    const uint32_t fh = filter_hash32(key);
+    const uint32_t mn = minimizer_of_key(key, k, tb_minimizer_m(k));
+    atomicOr(&filter[mini_word_index(mn, fh, sector_mask)], filter_bits<NBITS>(fh));
+}
+
 // ---- bitmap construction: one thread per table slot ---------------------------------
 __global__ void __launch_bounds__(256)
 k_filter_build(const unsigned long long *__restrict__ slots, uint64_t n_slots, uint32_t *filter,
@@ -658,7 +853,7 @@ k_finalize(tb_batch_view b, double scale_a, double scale_b)
 
 int g_unroll = 4;
 int g_tpb = 128;
-int g_filter_unroll = 16;
+int g_filter_unroll = 8;  // minimizer kernel: 8 (32 selects 4); hash-addressed kernels use 16
 int g_filter_mode = 2;
 
 template <int K>
@@ -702,6 +897,25 @@ cudaError_t launch_pair_k(const tb_batch_view &b, int k, tb_pair_view P, const u
         k_classify_pair<K, 16, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, word_mask, g_filter_mode);
     else
         k_classify_pair<K, 16, 1><<<blocks, tpb, 0, stream>>>(b, k, P, filter, word_mask, g_filter_mode);
+    return cudaGetLastError();
+}
+
+template <int K>
+cudaError_t launch_pair_mini_k(const tb_batch_view &b, int k, tb_pair_view P, const uint32_t *filter,
+                               uint32_t sector_mask, int n_bits, cudaStream_t stream)
+{
+    const int tpb = g_tpb;
+    const int warps = tpb / 32;
+    const unsigned blocks = (unsigned)((b.n_tiles + warps - 1) / warps);
+    if (n_bits == 2) {
+        switch (g_filter_unroll) {
+        case 32: k_classify_pair_mini<K, 4, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, sector_mask); break;
+        case 16: k_classify_pair_mini<K, 16, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, sector_mask); break;
+        default: k_classify_pair_mini<K, 8, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, sector_mask); break;
+        }
+    } else {
+        k_classify_pair_mini<K, 8, 1><<<blocks, tpb, 0, stream>>>(b, k, P, filter, sector_mask);
+    }
     return cudaGetLastError();
 }
 
@@ -779,6 +993,31 @@ cudaError_t tb_launch_classify_pair(const tb_batch_view &b, int k, tb_pair_view 
     case 31: return launch_pair_k<31>(b, k, P, filter, filter_word_mask, n_bits, stream);
     default: return launch_pair_k<0>(b, k, P, filter, filter_word_mask, n_bits, stream);
     }
+}
+
+cudaError_t tb_launch_classify_pair_mini(const tb_batch_view &b, int k, tb_pair_view P,
+                                         const uint32_t *filter, uint32_t sector_mask, int n_bits,
+                                         cudaStream_t stream)
+{
+    if (b.n_tiles == 0) return cudaSuccess;
+    switch (k) {
+    case 21: return launch_pair_mini_k<21>(b, k, P, filter, sector_mask, n_bits, stream);
+    case 31: return launch_pair_mini_k<31>(b, k, P, filter, sector_mask, n_bits, stream);
+    default: return launch_pair_mini_k<0>(b, k, P, filter, sector_mask, n_bits, stream);
+    }
+}
+
+cudaError_t tb_launch_pair_filter_build_mini(const uint64_t *d_pair_table, uint64_t n_slots, uint32_t *filter,
+                                             uint32_t sector_mask, int n_bits, int k, cudaStream_t stream)
+{
+    if (n_slots == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n_slots + 255) / 256);
+    const unsigned long long *slots = reinterpret_cast<const unsigned long long *>(d_pair_table);
+    if (n_bits == 2)
+        k_pair_filter_build_mini<2><<<blocks, 256, 0, stream>>>(slots, n_slots, filter, sector_mask, k);
+    else
+        k_pair_filter_build_mini<1><<<blocks, 256, 0, stream>>>(slots, n_slots, filter, sector_mask, k);
+    return cudaGetLastError();
 }
 
 cudaError_t tb_launch_pair_filter_build(const uint64_t *d_pair_table, uint64_t n_slots, uint32_t *filter,

@@ -133,6 +133,7 @@ lib.tb_classifier_rerun_resident.argtypes = [C.c_void_p, C.c_int, C.c_int,
 lib.tb_classifier_rerun_resident_flush.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64,
                                                    C.POINTER(C.c_float), C.POINTER(C.c_float)]
 lib.tb_classifier_filter_passes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+lib.tb_classifier_minimizer_mode.argtypes = [C.c_void_p]
 lib.tb_classifier_pair_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
 lib.tb_classifier_filter_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
 lib.tb_classifier_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
@@ -545,7 +546,8 @@ class Classifier:
         nb, nd, bits = C.c_uint32(), C.c_uint64(), C.c_int()
         _check(lib.tb_classifier_pair_info(self._h, C.byref(nb), C.byref(nd), C.byref(bits)))
         return {"log2_bits": m.value, "build_ms": ms.value, "pair_buckets": nb.value,
-                "pair_distinct": nd.value, "bits_per_key": bits.value if nb.value else 1}
+                "pair_distinct": nd.value, "bits_per_key": bits.value if nb.value else 1,
+                "minimizer": bool(lib.tb_classifier_minimizer_mode(self._h))}
 
     def stats(self, slot: int) -> dict:
         w, p, f, launches = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
