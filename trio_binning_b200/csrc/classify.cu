@@ -685,38 +685,51 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
     uint32_t pass = 0;
     if (c.vmask) {
         if (K != 0 && c.clean) {
-            // ---- all bases valid: m-mer hashes straight from the two streams, sliding minimum
+            // ---- all bases valid: m-mer hashes straight from the two streams, sliding minimum.
+            // Two passes of 16 windows over the same unrolled body (the second on the span
+            // moved by 16 bases) keep the loop inside the instruction cache.
             constexpr uint32_t MMASK = MC == 16 ? 0xFFFFFFFFu : ((1u << (2 * MC)) - 1u);
-            uint32_t hm[32 + WC];
+            LaneCtx h = c;  // half-span view: window j of the half starts at base j of (f0,f1)
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+                uint32_t hm[16 + WC];
 #pragma unroll
-            for (int q = 0; q < WC - 1; q++) {
-                const uint32_t f = (uint32_t)extract128(c.f0, c.f1, 2 * q) & MMASK;
-                const uint32_t r = (uint32_t)extract128(c.r_lo, c.r_hi, 2 * (64 - q - MC)) & MMASK;
-                hm[q] = mmer_mix(f < r ? f : r);
-            }
-#pragma unroll
-            for (int g = 0; g < 32; g += U) {
-                uint32_t need[U], wd[U], widx[U];
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const int j = g + u, q = j + WC - 1;
-                    {
-                        const uint32_t f = (uint32_t)extract128(c.f0, c.f1, 2 * q) & MMASK;
-                        const uint32_t r = (uint32_t)extract128(c.r_lo, c.r_hi, 2 * (64 - q - MC)) & MMASK;
-                        hm[q] = mmer_mix(f < r ? f : r);
-                    }
-                    uint32_t mn = hm[j];
-#pragma unroll
-                    for (int t = 1; t + 1 < WC; t += 2) mn = __vimin3_u32(mn, hm[j + t], hm[j + t + 1]);
-                    if ((WC & 1) == 0) mn = min(mn, hm[j + WC - 1]);
-                    const uint32_t fh = filter_hash32(window_key<K>(c, j, k, kmask));
-                    need[u] = filter_bits<NBITS>(fh);
-                    widx[u] = mini_word_index(mn, fh, sector_mask);
+                for (int q = 0; q < WC - 1; q++) {
+                    const uint32_t f = (uint32_t)extract128(h.f0, h.f1, 2 * q) & MMASK;
+                    const uint32_t r = (uint32_t)extract128(h.r_lo, h.r_hi, 2 * (64 - q - MC)) & MMASK;
+                    hm[q] = mmer_mix(f < r ? f : r);
                 }
+                uint32_t half_pass = 0;
 #pragma unroll
-                for (int u = 0; u < U; u++) wd[u] = ld_filter_l1(filter + widx[u], keep_policy);
+                for (int g = 0; g < 16; g += U) {
+                    uint32_t need[U], wd[U], widx[U];
 #pragma unroll
-                for (int u = 0; u < U; u++) pass |= ((wd[u] & need[u]) == need[u] ? 1u : 0u) << (g + u);
+                    for (int u = 0; u < U; u++) {
+                        const int j = g + u, q = j + WC - 1;
+                        {
+                            const uint32_t f = (uint32_t)extract128(h.f0, h.f1, 2 * q) & MMASK;
+                            const uint32_t r = (uint32_t)extract128(h.r_lo, h.r_hi, 2 * (64 - q - MC)) & MMASK;
+                            hm[q] = mmer_mix(f < r ? f : r);
+                        }
+                        uint32_t mn = hm[j];
+#pragma unroll
+                        for (int t = 1; t + 1 < WC; t += 2) mn = __vimin3_u32(mn, hm[j + t], hm[j + t + 1]);
+                        if ((WC & 1) == 0) mn = min(mn, hm[j + WC - 1]);
+                        const uint32_t fh = filter_hash32(window_key<K>(h, j, k, kmask));
+                        need[u] = filter_bits<NBITS>(fh);
+                        widx[u] = mini_word_index(mn, fh, sector_mask);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u++) wd[u] = ld_filter_l1(filter + widx[u], keep_policy);
+#pragma unroll
+                    for (int u = 0; u < U; u++) half_pass |= ((wd[u] & need[u]) == need[u] ? 1u : 0u) << (g + u);
+                }
+                pass |= half_pass << (16 * half);
+                // next half: drop 16 bases from the front of the span (and of its reverse complement)
+                h.f0 = (h.f0 >> 32) | (h.f1 << 32);
+                h.f1 >>= 32;
+                h.r_hi = (h.r_hi << 32) | (h.r_lo >> 32);
+                h.r_lo <<= 32;
             }
         } else {
             // ---- a non-ACGT base nearby (or an unusual k): minimizer from the key itself
