@@ -1,9 +1,9 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 V="python tools/kernel_variants.py"
-( $V 10000000 10000 20000; TB_FILTER_UNROLL=32 $V 10000000 10000 20000; TB_FILTER_UNROLL=16 $V 10000000 10000 20000
-  $V 150000000 10000 20000; TB_FILTER_UNROLL=32 $V 150000000 10000 20000; TB_FILTER_UNROLL=16 $V 150000000 10000 20000
-  K=31 $V 400000000 10000 20000; K=31 TB_FILTER_UNROLL=32 $V 400000000 10000 20000
-  $V 50000000 2000000 150 fixed ) 2>&1 | grep -v "^Found\|^Done\|^Reading" | sed -e 's/ lf=0.5 buckets=[0-9]*//' -e 's/UNROLL=[0-9]* TPB=128 L2G=32: //' -e 's/table_MB=[0-9x]* //' -e 's/(build.*//' | tee gpurun_out/halves.log
+( $V 10000000 10000 20000; TB_FILTER_UNROLL=32 $V 10000000 10000 20000
+  $V 150000000 10000 20000
+  K=31 $V 400000000 10000 20000
+  $V 50000000 2000000 150 fixed ) 2>&1 | grep -v "^Found\|^Done\|^Reading" | sed -e 's/ lf=0.5 buckets=[0-9]*//' -e 's/UNROLL=[0-9]* TPB=128 L2G=32: //' -e 's/table_MB=[0-9x]* //' -e 's/(build.*//' | tee gpurun_out/fma.log
