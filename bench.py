@@ -494,6 +494,13 @@ def run_gpu_arm(args, rank, local_rank, world):
             if t:
                 roofline["traffic"] = t["dram_bytes_per_launch"]
                 roofline["traffic_source"] = t["source"]
+                if "alu_pipe_pct" in t:
+                    roofline["ncu_alu_pipe_pct"] = t["alu_pipe_pct"]
+                    roofline["ncu_l1_sector_hit_pct"] = t["l1_sector_hit_pct"]
+                    roofline["note"] += (
+                        "; frac can exceed 1.0 here: the ceiling is for sector requests that bypass L1, while the "
+                        "minimizer-addressed sectors let L1 serve %.0f%% of them -- per ncu the kernel is bound by the "
+                        "integer ALU pipe (%.0f%% of peak), not by memory" % (t["l1_sector_hit_pct"], t["alu_pipe_pct"]))
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             kind = cpu_reference_setup(wl)
