@@ -92,13 +92,30 @@ k_pack(tb_batch_view b, int k)
         const uint4 *src = reinterpret_cast<const uint4 *>(b.ascii + p0);
         uint4 q0 = __ldg(src), q1 = __ldg(src + 1);
         uint32_t x[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
-        vmask = 0;
+        // Fast path: take the two code bits of every byte as if it were a base, rebuild the
+        // letter those bits stand for (A 0x41, C 0x43, G 0x47, T 0x54 = 0x41 + 2c + 2*[c>=2]
+        // + 11*[c==3], four bytes at a time, no carries) and compare with the input: any
+        // difference in the 32 bytes sends the word to the exact per-byte path below.
+        uint32_t any_diff = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            uint32_t c, v;
-            pack4(x[i], c, v);
-            f |= (uint64_t)c << (8 * i);
-            vmask |= v << (4 * i);
+            const uint32_t u = (x[i] >> 1) ^ (x[i] >> 2);
+            const uint32_t t = u & 0x03030303u;
+            const uint32_t b1 = (u >> 1) & 0x01010101u;
+            const uint32_t expect = 0x41414141u + 2u * t + 2u * b1 + 11u * (b1 & u);
+            any_diff |= expect ^ x[i];
+            f |= (uint64_t)((t | (t >> 6) | (t >> 12) | (t >> 18)) & 0xFFu) << (8 * i);
+        }
+        if (any_diff) {
+            f = 0;
+            vmask = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                uint32_t c, v;
+                pack4(x[i], c, v);
+                f |= (uint64_t)c << (8 * i);
+                vmask |= v << (4 * i);
+            }
         }
     } else if (p0 < b.total_bases) {
         int n = (int)(b.total_bases - p0);
