@@ -400,7 +400,7 @@ int enqueue_kernels(tb_classifier *c, Slot &s, cudaEvent_t before_classify, cuda
     if (before_classify) CK(cudaEventRecord(before_classify, s.stream));
     if (c->d_pair && c->d_filter && c->mini) {
         tb_pair_view P = { c->d_pair, c->pair_buckets };
-        CK(tb_launch_classify_pair_mini(s.view, c->k, P, c->d_filter, c->filter_word_mask >> 3, c->filter_bits, s.stream));
+        CK(tb_launch_classify_pair_mini(s.view, c->k, P, c->d_filter, (c->filter_word_mask >> 3) + 1, c->filter_bits, s.stream));
     } else if (c->d_pair && c->d_filter) {
         tb_pair_view P = { c->d_pair, c->pair_buckets };
         CK(tb_launch_classify_pair(s.view, c->k, P, c->d_filter, c->filter_word_mask, c->filter_bits, s.stream));
@@ -474,7 +474,7 @@ int build_filter(tb_classifier *c)
         c->filter_bits = nbits;
         if (c->mini)
             CK(tb_launch_pair_filter_build_mini(reinterpret_cast<const uint64_t *>(c->d_pair), nb * TB_SLOTS,
-                                                c->d_filter, c->filter_word_mask >> 3, nbits, c->k, 0));
+                                                c->d_filter, (c->filter_word_mask >> 3) + 1, nbits, c->k, 0));
         else
             CK(tb_launch_pair_filter_build(reinterpret_cast<const uint64_t *>(c->d_pair), nb * TB_SLOTS,
                                            c->d_filter, c->filter_word_mask, nbits, 0));
@@ -888,7 +888,7 @@ int tb_classifier_submit_packed(tb_classifier *c, int slot, const tb_packed_batc
                               pb->n_ub, st));
     if (c->d_pair && c->d_filter && c->mini) {
         tb_pair_view P = { c->d_pair, c->pair_buckets };
-        CK(tb_launch_classify_pair_mini(v, c->k, P, c->d_filter, c->filter_word_mask >> 3, c->filter_bits, st));
+        CK(tb_launch_classify_pair_mini(v, c->k, P, c->d_filter, (c->filter_word_mask >> 3) + 1, c->filter_bits, st));
     } else if (c->d_pair && c->d_filter) {
         tb_pair_view P = { c->d_pair, c->pair_buckets };
         CK(tb_launch_classify_pair(v, c->k, P, c->d_filter, c->filter_word_mask, c->filter_bits, st));

@@ -670,11 +670,13 @@ __device__ __forceinline__ uint32_t filter_hash32(uint64_t key)
 }
 
 // word index of a key's bitmap word: sector from the minimizer, word in the sector from the k-mer
-__device__ __forceinline__ uint32_t mini_word_index(uint32_t min_hash, uint32_t fh, uint32_t sector_mask)
+// (range reduction and the *8 + word go through IMAD.HI / IMAD: the FMA pipe is idle, the ALU
+// pipe is what bounds the kernel)
+__device__ __forceinline__ uint32_t mini_word_index(uint32_t min_hash, uint32_t fh, uint32_t n_sectors)
 {
     uint32_t s = min_hash * 0xC2B2AE35u;  // the minimum of several hashes is biased small: re-spread
     s ^= s >> 16;
-    return ((s & sector_mask) << 3) | ((fh >> 10) & 7u);
+    return __umulhi(s, n_sectors) * 8u + ((fh >> 10) & 7u);
 }
 
 __device__ __forceinline__ uint32_t ld_filter_l1(const uint32_t *p, uint64_t policy)
@@ -690,7 +692,7 @@ __device__ __forceinline__ uint32_t ld_filter_l1(const uint32_t *p, uint64_t pol
 template <int K, int U, int NBITS>
 __global__ void __launch_bounds__(128, TB_MINI_MIN_BLOCKS)
 k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint32_t *__restrict__ filter,
-                     uint32_t sector_mask)
+                     uint32_t n_sectors)
 {
     const int k = K ? K : k_runtime;
     const int m = tb_minimizer_m(k);
@@ -740,7 +742,7 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
                         if ((WC & 1) == 0) mn = min(mn, hm[j + WC - 1]);
                         const uint32_t fh = filter_hash32(window_key<K>(h, j, k, kmask));
                         need[u] = filter_bits<NBITS>(fh);
-                        widx[u] = mini_word_index(mn, fh, sector_mask);
+                        widx[u] = mini_word_index(mn, fh, n_sectors);
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) wd[u] = ld_filter_l1(filter + widx[u], keep_policy);
@@ -762,7 +764,7 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
                 const uint64_t key = window_key<0>(c, j, k, kmask);
                 const uint32_t fh = filter_hash32(key);
                 const uint32_t need = filter_bits<NBITS>(fh);
-                const uint32_t wd = ld_filter_l1(filter + mini_word_index(minimizer_of_key(key, k, m), fh, sector_mask),
+                const uint32_t wd = ld_filter_l1(filter + mini_word_index(minimizer_of_key(key, k, m), fh, n_sectors),
                                                  keep_policy);
                 pass |= ((wd & need) == need ? 1u : 0u) << j;
             }
@@ -807,7 +809,7 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
 template <int NBITS>
 __global__ void __launch_bounds__(256)
 k_pair_filter_build_mini(const unsigned long long *__restrict__ slots, uint64_t n_slots, uint32_t *filter,
-                         uint32_t sector_mask, int k)
+                         uint32_t n_sectors, int k)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_slots) return;
@@ -816,7 +818,7 @@ k_pair_filter_build_mini(const unsigned long long *__restrict__ slots, uint64_t 
     const uint64_t key = e & TB_PAIR_KEYMASK;
     const uint32_t fh = filter_hash32(key);
     const uint32_t mn = minimizer_of_key(key, k, tb_minimizer_m(k));
-    atomicOr(&filter[mini_word_index(mn, fh, sector_mask)], filter_bits<NBITS>(fh));
+    atomicOr(&filter[mini_word_index(mn, fh, n_sectors)], filter_bits<NBITS>(fh));
 }
 
 // ---- bitmap construction: one thread per table slot ---------------------------------
@@ -939,19 +941,19 @@ cudaError_t launch_pair_k(const tb_batch_view &b, int k, tb_pair_view P, const u
 
 template <int K>
 cudaError_t launch_pair_mini_k(const tb_batch_view &b, int k, tb_pair_view P, const uint32_t *filter,
-                               uint32_t sector_mask, int n_bits, cudaStream_t stream)
+                               uint32_t n_sectors, int n_bits, cudaStream_t stream)
 {
     const int tpb = g_tpb;
     const int warps = tpb / 32;
     const unsigned blocks = (unsigned)((b.n_tiles + warps - 1) / warps);
     if (n_bits == 2) {
         switch (g_filter_unroll) {
-        case 32: k_classify_pair_mini<K, 4, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, sector_mask); break;
-        case 16: k_classify_pair_mini<K, 16, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, sector_mask); break;
-        default: k_classify_pair_mini<K, 8, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, sector_mask); break;
+        case 32: k_classify_pair_mini<K, 4, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors); break;
+        case 16: k_classify_pair_mini<K, 16, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors); break;
+        default: k_classify_pair_mini<K, 8, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors); break;
         }
     } else {
-        k_classify_pair_mini<K, 8, 1><<<blocks, tpb, 0, stream>>>(b, k, P, filter, sector_mask);
+        k_classify_pair_mini<K, 8, 1><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors);
     }
     return cudaGetLastError();
 }
@@ -1033,27 +1035,27 @@ cudaError_t tb_launch_classify_pair(const tb_batch_view &b, int k, tb_pair_view 
 }
 
 cudaError_t tb_launch_classify_pair_mini(const tb_batch_view &b, int k, tb_pair_view P,
-                                         const uint32_t *filter, uint32_t sector_mask, int n_bits,
+                                         const uint32_t *filter, uint32_t n_sectors, int n_bits,
                                          cudaStream_t stream)
 {
     if (b.n_tiles == 0) return cudaSuccess;
     switch (k) {
-    case 21: return launch_pair_mini_k<21>(b, k, P, filter, sector_mask, n_bits, stream);
-    case 31: return launch_pair_mini_k<31>(b, k, P, filter, sector_mask, n_bits, stream);
-    default: return launch_pair_mini_k<0>(b, k, P, filter, sector_mask, n_bits, stream);
+    case 21: return launch_pair_mini_k<21>(b, k, P, filter, n_sectors, n_bits, stream);
+    case 31: return launch_pair_mini_k<31>(b, k, P, filter, n_sectors, n_bits, stream);
+    default: return launch_pair_mini_k<0>(b, k, P, filter, n_sectors, n_bits, stream);
     }
 }
 
 cudaError_t tb_launch_pair_filter_build_mini(const uint64_t *d_pair_table, uint64_t n_slots, uint32_t *filter,
-                                             uint32_t sector_mask, int n_bits, int k, cudaStream_t stream)
+                                             uint32_t n_sectors, int n_bits, int k, cudaStream_t stream)
 {
     if (n_slots == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n_slots + 255) / 256);
     const unsigned long long *slots = reinterpret_cast<const unsigned long long *>(d_pair_table);
     if (n_bits == 2)
-        k_pair_filter_build_mini<2><<<blocks, 256, 0, stream>>>(slots, n_slots, filter, sector_mask, k);
+        k_pair_filter_build_mini<2><<<blocks, 256, 0, stream>>>(slots, n_slots, filter, n_sectors, k);
     else
-        k_pair_filter_build_mini<1><<<blocks, 256, 0, stream>>>(slots, n_slots, filter, sector_mask, k);
+        k_pair_filter_build_mini<1><<<blocks, 256, 0, stream>>>(slots, n_slots, filter, n_sectors, k);
     return cudaGetLastError();
 }
 

@@ -83,10 +83,10 @@ cudaError_t tb_launch_pair_filter_build(const uint64_t *d_pair_table, uint64_t n
                                         uint32_t filter_word_mask, int n_bits, cudaStream_t stream);
 // minimizer-addressed variant for large sets: sector (8 words) chosen by the key's minimizer
 cudaError_t tb_launch_classify_pair_mini(const tb_batch_view &b, int k, tb_pair_view P,
-                                         const uint32_t *filter, uint32_t sector_mask, int n_bits,
+                                         const uint32_t *filter, uint32_t n_sectors, int n_bits,
                                          cudaStream_t stream);
 cudaError_t tb_launch_pair_filter_build_mini(const uint64_t *d_pair_table, uint64_t n_slots, uint32_t *filter,
-                                             uint32_t sector_mask, int n_bits, int k, cudaStream_t stream);
+                                             uint32_t n_sectors, int n_bits, int k, cudaStream_t stream);
 cudaError_t tb_launch_fixup(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
                             cudaStream_t stream);
 cudaError_t tb_launch_finalize(const tb_batch_view &b, double scale_a, double scale_b,
