@@ -1,15 +1,9 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-for n in 8 4 2; do
-echo "== bench N=$n"; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2952$n bench.py --gpus $n --steps 50 --warmup 3 > gpurun_out/bench_n$n.log 2> gpurun_out/bench_n$n.err; echo "rc=$?"; tail -1 gpurun_out/bench_n$n.log | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print('n_gpus', d['n_gpus'], 'value %.1f G' % (d['value']/1e9), 'e2e %.1f G via %s' % (d['e2e']['value']/1e9, d['e2e']['route']), 'ascii_device_pack %.1f G' % (d['e2e_variants']['ascii_device_pack']['value']/1e9), 'e2e_packed %.1f G' % (d['e2e_packed']['value']/1e9), 'ms/step %.3f' % d['ms_per_step'])
-"
-done
-echo "== bench N=1"; timeout 900 python bench.py > gpurun_out/bench_n1.log 2> gpurun_out/bench_n1.err; tail -1 gpurun_out/bench_n1.log | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print('n_gpus', d['n_gpus'], 'value %.1f G' % (d['value']/1e9), 'e2e %.1f G via %s' % (d['e2e']['value']/1e9, d['e2e']['route']), 'ascii_device_pack %.1f G' % (d['e2e_variants']['ascii_device_pack']['value']/1e9), 'e2e_packed %.1f G' % (d['e2e_packed']['value']/1e9), 'ms/step %.3f' % d['ms_per_step'], 'cpu', d['cpu_baseline']['value'])
-"
+echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+V="python tools/kernel_variants.py"
+( $V 10000000 10000 20000; TB_FILTER_UNROLL=32 $V 10000000 10000 20000; TB_FILTER_UNROLL=16 $V 10000000 10000 20000
+  $V 150000000 10000 20000
+  K=31 $V 400000000 10000 20000
+  $V 50000000 2000000 150 fixed ) 2>&1 | grep -v "^Found\|^Done\|^Reading" | sed -e 's/ lf=0.5 buckets=[0-9]*//' -e 's/UNROLL=[0-9]* //' -e 's/ L2G=32: / /' -e 's/table_MB=[0-9x]* //' -e 's/(build.*//' | tee gpurun_out/v.log

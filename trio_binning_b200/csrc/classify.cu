@@ -624,7 +624,14 @@ k_pair_filter_build(const unsigned long long *__restrict__ slots, uint64_t n_slo
 // (15/16) that many minimizer values share a sector, which evens out the skew of minimizer
 // popularity.  The minimizer is a pure function of the key VALUE, so stored keys (raw, Q1)
 // and looked-up keys agree whatever strand or scratch quirk produced them.
-__host__ __device__ __forceinline__ int tb_minimizer_m(int k) { return k >= 22 ? 16 : (k >= 7 ? k - 6 : 1); }
+// m: 16 for k >= 22, else k-6 but at least k/2 so that the first and the last m-mer of a
+// k-mer together cover all of its bases (their hashes also address the word and the bits)
+__host__ __device__ __forceinline__ int tb_minimizer_m(int k)
+{
+    if (k >= 22) return 16;
+    const int a = k - 6, b = (k + 1) / 2;
+    return a > b ? a : b;
+}
 
 __device__ __forceinline__ uint32_t mmer_mix(uint32_t c)
 {
@@ -643,30 +650,33 @@ __device__ __forceinline__ uint32_t mmer_revcomp(uint32_t f, int m)
     return x >> (32 - 2 * m);
 }
 
-// smallest hash over the canonical m-mers of a k-mer given as its integer key
-__device__ __forceinline__ uint32_t minimizer_of_key(uint64_t key, int k, int m)
+// Bitmap coordinates of a k-mer, as pure functions of its integer key:
+//   min_hash  smallest hash over its canonical m-mers (the minimizer) -> the sector
+//   fh        hash of the first canonical m-mer + hash of the last one -> word in the sector and
+//             the bit positions.  The two m-mers cover the whole k-mer (2m >= k), the sum is
+//             symmetric under reverse complement (first and last swap), and in the kernel both
+//             terms are already in the sliding window of m-mer hashes: phase 1 needs no k-mer
+//             key at all, only m-mers.
+struct KmerCoord {
+    uint32_t min_hash, fh;
+};
+
+__device__ __forceinline__ KmerCoord coord_of_key(uint64_t key, int k, int m)
 {
     const uint32_t mmask = m == 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
-    uint32_t best = 0xFFFFFFFFu;
+    KmerCoord c;
+    c.min_hash = 0xFFFFFFFFu;
+    uint32_t first = 0, last = 0;
     for (int i = 0; i + m <= k; i++) {
         const uint32_t f = (uint32_t)(key >> (2 * i)) & mmask;
         const uint32_t r = mmer_revcomp(f, m);
         const uint32_t h = mmer_mix(f < r ? f : r);
-        best = h < best ? h : best;
+        c.min_hash = h < c.min_hash ? h : c.min_hash;
+        if (i == 0) first = h;
+        last = h;
     }
-    return best;
-}
-
-// 13 well-mixed bits of the key are all phase 1 needs (word in the sector + bit positions):
-// a two-multiply 32-bit mixer instead of the 64-bit one (the pair bucket is only computed
-// for the few survivors, in phase 2)
-__device__ __forceinline__ uint32_t filter_hash32(uint64_t key)
-{
-    uint32_t x = (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA77u;
-    x ^= x >> 15;
-    x *= 0x2C1B3C6Du;
-    x ^= x >> 13;
-    return x;
+    c.fh = first + last;
+    return c;
 }
 
 // word index of a key's bitmap word: sector from the minimizer, word in the sector from the k-mer
@@ -740,7 +750,7 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
 #pragma unroll
                         for (int t = 1; t + 1 < WC; t += 2) mn = __vimin3_u32(mn, hm[j + t], hm[j + t + 1]);
                         if ((WC & 1) == 0) mn = min(mn, hm[j + WC - 1]);
-                        const uint32_t fh = filter_hash32(window_key<K>(h, j, k, kmask));
+                        const uint32_t fh = hm[j] + hm[j + WC - 1];  // first + last m-mer of the window
                         need[u] = filter_bits<NBITS>(fh);
                         widx[u] = mini_word_index(mn, fh, n_sectors);
                     }
@@ -761,11 +771,9 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
             // ---- a non-ACGT base nearby (or an unusual k): minimizer from the key itself
             for (int j = 0; j < 32; j++) {
                 if (!((c.vmask >> j) & 1u)) continue;
-                const uint64_t key = window_key<0>(c, j, k, kmask);
-                const uint32_t fh = filter_hash32(key);
-                const uint32_t need = filter_bits<NBITS>(fh);
-                const uint32_t wd = ld_filter_l1(filter + mini_word_index(minimizer_of_key(key, k, m), fh, n_sectors),
-                                                 keep_policy);
+                const KmerCoord kc = coord_of_key(window_key<0>(c, j, k, kmask), k, m);
+                const uint32_t need = filter_bits<NBITS>(kc.fh);
+                const uint32_t wd = ld_filter_l1(filter + mini_word_index(kc.min_hash, kc.fh, n_sectors), keep_policy);
                 pass |= ((wd & need) == need ? 1u : 0u) << j;
             }
         }
@@ -815,10 +823,8 @@ k_pair_filter_build_mini(const unsigned long long *__restrict__ slots, uint64_t 
     if (i >= n_slots) return;
     const unsigned long long e = slots[i];
     if (e == 0) return;
-    const uint64_t key = e & TB_PAIR_KEYMASK;
-    const uint32_t fh = filter_hash32(key);
-    const uint32_t mn = minimizer_of_key(key, k, tb_minimizer_m(k));
-    atomicOr(&filter[mini_word_index(mn, fh, n_sectors)], filter_bits<NBITS>(fh));
+    const KmerCoord kc = coord_of_key(e & TB_PAIR_KEYMASK, k, tb_minimizer_m(k));
+    atomicOr(&filter[mini_word_index(kc.min_hash, kc.fh, n_sectors)], filter_bits<NBITS>(kc.fh));
 }
 
 // ---- bitmap construction: one thread per table slot ---------------------------------
