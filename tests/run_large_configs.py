@@ -1,6 +1,8 @@
 """BASELINE.json configs[2..4] at full SET sizes on one GPU (reads: a slice of the stated shape).
 Prints one JSON line per config: sizes, filter/pair info, kernel time, throughput, parity check.
-usage: run_configs.py [c3] [c4] [c5]"""
+usage: python tests/run_large_configs.py [c3] [c4] [c5]
+(kept under tests/ because it checks against the oracle; not collected by pytest: it needs
+minutes of GPU-box time and tens of GB of host memory)"""
 import json
 import os
 import sys
