@@ -143,7 +143,7 @@ int tb_classifier_submit(tb_classifier *c, int slot,
 int tb_classifier_wait(tb_classifier *c, int slot);
 /* ---- host-packed batches (north_star: "pinned, 2-bit-packed batches") -------------
  * tb_pack_reads converts concatenated ASCII reads into the flat 2-bit layout the
- * classify kernels consume, on the host (multi-threaded, AVX2), so that 0.25 byte per
+ * classify kernels consume, on the host (multi-threaded, AVX2 / AVX-512), so that 0.25 byte per
  * base crosses PCIe.  All arrays are caller-owned (pinned memory from tb_host_alloc for
  * asynchronous copies); cap_* are their capacities, the n_* fields are outputs.
  *   F          cap_words  u64: >= (ceil(total/1024)+1)*32
@@ -221,14 +221,15 @@ int tb_classifier_rerun_resident_flush(tb_classifier *c, int slot, int iters, ui
 /* Number of windows of the slot's last batch whose pre-filter bit was set (they are the
  * only ones that probed the tables in HBM); 0 when the direct kernel is in use. */
 int tb_classifier_filter_passes(tb_classifier *c, int slot, uint64_t *n_pass);
-/* The classifier's L2-resident pre-filter: log2 of its size in bits (0 = none, the
- * direct kernel is used) and the device time spent building it. */
+/* The classifier's bitmap pre-filter: log2 of its size in bits (0 = none, the direct
+ * kernel is used) and the device time spent building it and the pair table. */
 int tb_classifier_filter_info(tb_classifier *c, int *log2_bits, float *build_ms);
 /* The classifier's pair table (one tagged table for both sets, k <= 31; TB_PAIR=0 turns it
  * off): buckets (0 = none), distinct keys of A u B, bitmap bits set per key. */
 int tb_classifier_pair_info(tb_classifier *c, uint32_t *n_buckets, uint64_t *n_distinct, int *filter_bits);
-/* 1 if the classifier's bitmap sectors are addressed by the keys' minimizers (the mode for
- * sets too large for an L2-resident bitmap; TB_MINIMIZER=0|1 forces it). */
+/* 1 if the classifier's bitmap sectors are addressed by the keys' minimizers, so that
+ * consecutive windows of a read re-use sectors from L1 (default whenever the pair table
+ * exists, i.e. k <= 31; TB_MINIMIZER=0 selects hash-addressed words). */
 int tb_classifier_minimizer_mode(tb_classifier *c);
 /* Counters of the last batch in a slot: windows, probes as the reference performs
  * them (W + (W - hits_A)), reads that took the Q3-UB fix-up path. */
