@@ -102,7 +102,7 @@ int use_device(int device)
             }
         }
         cudaGetLastError();
-        tb_classify_config(env_int("TB_UNROLL", 4), env_int("TB_TPB", 128), env_int("TB_FILTER_UNROLL", 8),
+        tb_classify_config(env_int("TB_UNROLL", 4), env_int("TB_TPB", 128), env_int("TB_FILTER_UNROLL", 16),
                             env_int("TB_FILTER_MODE", 2));
         g_device_ready[device] = true;
     }

@@ -898,7 +898,7 @@ k_finalize(tb_batch_view b, double scale_a, double scale_b)
 
 int g_unroll = 4;
 int g_tpb = 128;
-int g_filter_unroll = 8;  // minimizer kernel: 8 (32 selects 4); hash-addressed kernels use 16
+int g_filter_unroll = 16;  // hash-addressed filtered kernel (k = 32 or TB_PAIR=0)
 int g_filter_mode = 2;
 
 template <int K>
@@ -952,15 +952,11 @@ cudaError_t launch_pair_mini_k(const tb_batch_view &b, int k, tb_pair_view P, co
     const int tpb = g_tpb;
     const int warps = tpb / 32;
     const unsigned blocks = (unsigned)((b.n_tiles + warps - 1) / warps);
-    if (n_bits == 2) {
-        switch (g_filter_unroll) {
-        case 32: k_classify_pair_mini<K, 4, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors); break;
-        case 16: k_classify_pair_mini<K, 16, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors); break;
-        default: k_classify_pair_mini<K, 8, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors); break;
-        }
-    } else {
+    // 8 bitmap loads in flight per lane; 4 and 16 measured the same (profiles/r1_kernel_variants_minimizer*.txt)
+    if (n_bits == 2)
+        k_classify_pair_mini<K, 8, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors);
+    else
         k_classify_pair_mini<K, 8, 1><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors);
-    }
     return cudaGetLastError();
 }
 
