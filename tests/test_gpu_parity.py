@@ -564,3 +564,34 @@ def test_reference_style_ctypes_binding(kmers):
     m = max(a.contents.num_kmers, b.contents.num_kmers)
     sa, sb = 1.0 * m / a.contents.num_kmers, 1.0 * m / b.contents.num_kmers
     assert (ca.value * sa, cb.value * sb) == (2.0, 4 / 3)
+
+
+# ---------------------------------------------------------------- error behaviour
+def test_api_misuse_fails_loudly(kmers, fixture_sets):
+    a, b = fixture_sets
+    bases = np.frombuffer(b"ACGT" * 100, dtype=np.uint8)
+    offsets = np.array([0, 400], dtype=np.int64)
+    with kmers.Classifier(a, b, max_bases=100, max_reads=4, n_slots=1) as clf:
+        with pytest.raises(ValueError):
+            clf.submit(0, bases, offsets)                      # larger than the slot
+        rc = kmers.lib.tb_classifier_submit(clf._h, 3, None, None, 0, None, None, None, None, None)
+        assert rc != 0 and b"slot" in kmers.lib.tb_last_error()
+        rc = kmers.lib.tb_classifier_rerun_resident(clf._h, 0, 1, None, None)
+        assert rc != 0 and b"no batch" in kmers.lib.tb_last_error()
+    with pytest.raises(RuntimeError, match="non-decreasing|offsets"):
+        kmers.classify_packed(bases, np.array([0, 300, 200, 400], dtype=np.int64), a, b)
+    with pytest.raises(RuntimeError):
+        kmers.create_kmer_hash_set_from_ints(np.zeros(0, dtype=np.uint64), 21)
+    with pytest.raises(RuntimeError):
+        kmers.create_kmer_hash_set_from_ints(np.arange(10, dtype=np.uint64), 40)
+    with pytest.raises(RuntimeError):
+        kmers.set_device(99)
+    # a destroyed set is rejected instead of being dereferenced
+    s = kmers.create_kmer_hash_set_from_ints(np.arange(10, dtype=np.uint64), 21)
+    import ctypes as C
+
+    shadow = C.cast(C.pointer(kmers._HashSet.from_buffer_copy(s.contents)), kmers.HashSet)
+    kmers.destroy_kmer_hash_set(s)
+    shadow.contents.magic = 0
+    with pytest.raises(RuntimeError, match="invalid set"):
+        kmers.classify_packed(bases, offsets, shadow, shadow)
