@@ -727,14 +727,30 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
             // moved by 16 bases) keep the loop inside the instruction cache.
             constexpr uint32_t MMASK = MC == 16 ? 0xFFFFFFFFu : ((1u << (2 * MC)) - 1u);
             LaneCtx h = c;  // half-span view: window j of the half starts at base j of (f0,f1)
+            // m-mer hashes of the first WC-1 positions of a half; for short rings the second half
+            // inherits them from the first (its positions 16 .. 16+WC-2); for k = 31 (15 carried
+            // registers) recomputing them is cheaper than the spills
+            constexpr bool CARRY = WC <= 8;
+            uint32_t head[WC > 1 ? WC - 1 : 1];
+#pragma unroll
+            for (int q = 0; q < WC - 1; q++) {
+                const uint32_t f = (uint32_t)extract128(h.f0, h.f1, 2 * q) & MMASK;
+                const uint32_t r = (uint32_t)extract128(h.r_lo, h.r_hi, 2 * (64 - q - MC)) & MMASK;
+                head[q] = mmer_mix(f < r ? f : r);
+            }
 #pragma unroll 1
             for (int half = 0; half < 2; half++) {
                 uint32_t hm[16 + WC];
+                if (CARRY || half == 0) {
 #pragma unroll
-                for (int q = 0; q < WC - 1; q++) {
-                    const uint32_t f = (uint32_t)extract128(h.f0, h.f1, 2 * q) & MMASK;
-                    const uint32_t r = (uint32_t)extract128(h.r_lo, h.r_hi, 2 * (64 - q - MC)) & MMASK;
-                    hm[q] = mmer_mix(f < r ? f : r);
+                    for (int q = 0; q < WC - 1; q++) hm[q] = head[q];
+                } else {
+#pragma unroll
+                    for (int q = 0; q < WC - 1; q++) {
+                        const uint32_t f = (uint32_t)extract128(h.f0, h.f1, 2 * q) & MMASK;
+                        const uint32_t r = (uint32_t)extract128(h.r_lo, h.r_hi, 2 * (64 - q - MC)) & MMASK;
+                        hm[q] = mmer_mix(f < r ? f : r);
+                    }
                 }
                 uint32_t half_pass = 0;
 #pragma unroll
@@ -763,6 +779,10 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
                         if ((need[u] & ~wd[u]) == 0) half_pass |= 1u << (g + u);
                 }
                 pass |= half_pass << (16 * half);
+                if (CARRY) {
+#pragma unroll
+                    for (int q = 0; q < WC - 1; q++) head[q] = hm[16 + q];
+                }
                 // next half: drop 16 bases from the front of the span (and of its reverse complement)
                 h.f0 = (h.f0 >> 32) | (h.f1 << 32);
                 h.f1 >>= 32;
