@@ -595,3 +595,32 @@ def test_api_misuse_fails_loudly(kmers, fixture_sets):
     shadow.contents.magic = 0
     with pytest.raises(RuntimeError, match="invalid set"):
         kmers.classify_packed(bases, offsets, shadow, shadow)
+
+
+# ---------------------------------------------------------------- short-read shape at volume
+@pytest.mark.parametrize("k", [21, 31])
+def test_short_read_volume_vs_oracle_subsample(kmers, oracle, k):
+    """BASELINE configs[4] shape (150-bp reads, hundreds of thousands of them: every lane of the
+    kernel straddles read boundaries) against 2 M + 2 M keys; the oracle checks every 100th read
+    and the total of the counts must survive a shuffle of the batch."""
+    from trio_binning_b200 import synth
+
+    ka, kb = synth.random_kmer_sets(2_000_000, 2_000_000, k, seed=900 + k)
+    n = 400_000
+    bases, offsets, _ = synth.random_reads(n, 150, k, ka, kb, seed=k, plant_every=60, fixed_len=True,
+                                           invalid_rate=0.0005)
+    A = kmers.create_kmer_hash_set_from_ints(ka, k)
+    B = kmers.create_kmer_hash_set_from_ints(kb, k)
+    ca, cb, *_ = kmers.classify_packed(bases, offsets, A, B)
+    oa, ob = oracle.set_from_ints(ka, k), oracle.set_from_ints(kb, k)
+    for r in range(0, n, 100):
+        assert oracle.count(bytes(bases[offsets[r]:offsets[r + 1]]), oa, ob) == (ca[r], cb[r]), r
+    assert ca.sum() > 50_000 and cb.sum() > 50_000
+    perm = np.random.default_rng(1).permutation(n)
+    shuffled = bases.reshape(n, 150)[perm].reshape(-1)
+    sa, sb, *_ = kmers.classify_packed(shuffled, offsets, A, B)
+    assert (sa == ca[perm]).all() and (sb == cb[perm]).all()
+    oracle.set_free(oa)
+    oracle.set_free(ob)
+    kmers.destroy_kmer_hash_set(A)
+    kmers.destroy_kmer_hash_set(B)
