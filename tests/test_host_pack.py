@@ -94,3 +94,84 @@ def test_pack_empty_and_capacity(kmers):
     big = np.full(10000, ord("A"), dtype=np.uint8)
     with pytest.raises(RuntimeError):
         pb.pack(big, np.array([0, 10000], dtype=np.int64), 21)
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+@pytest.mark.parametrize("misalign", [0, 8])
+def test_pack_clean_runs_and_block_edges(kmers, threads, misalign):
+    """Long clean stretches take the 256-base block loop; junk placed on, before and after block
+    and tile edges (and in the last, partial block) must stop it at the right word and hand over
+    to the word path, and the loop must resume afterwards.  F is placed at a 64-byte aligned
+    address (streaming stores, as with pinned buffers) or 8 bytes past one (plain stores)."""
+    rng = np.random.default_rng(77 + threads)
+    lens = [300_000, 0, 1, 255, 256, 257, 70_000, 33]
+    total = sum(lens)
+    bases = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, total)].copy()
+    junk_at = [0, 255, 256, 257, 511, 1023, 1024, 1025, 8191, 8192, 100_000, 100_031, 100_032,
+               299_999, 300_000, 300_600, total - 300, total - 33, total - 1]
+    junk_at += [int(x) for x in rng.integers(0, total, 12)]
+    bases[junk_at] = np.frombuffer(b"Nn\x80\xff@Q", dtype=np.uint8)[rng.integers(0, 6, len(junk_at))]
+    offsets = np.zeros(len(lens) + 1, dtype=np.int64)
+    offsets[1:] = np.cumsum(lens)
+    pb = kmers.PackedBatch(total + 4096, len(lens) + 2, pinned=False)
+    big = np.zeros(pb.cap["words"] + 16, dtype=np.uint64)
+    off = ((misalign - big.ctypes.data) % 64) // 8
+    view = big[off:off + pb.cap["words"]]
+    assert view.ctypes.data % 64 == misalign
+    pb.F.array, pb.F.ptr = view, view.ctypes.data
+    pb.c.F = view.ctypes.data
+    pb.pack(bases, offsets, 21, threads=threads)
+    n_words = (total + 31) // 32
+    padded = np.zeros(n_words * 32, dtype=np.uint8)
+    padded[:total] = orc_mod._CODE[bases]
+    want = (padded.reshape(n_words, 32).astype(np.uint64) << (2 * np.arange(32, dtype=np.uint64))).sum(
+        axis=1, dtype=np.uint64)
+    assert (pb.F.array[:n_words] == want).all()
+    vpad = np.ones(n_words * 32, dtype=bool)
+    vpad[:total] = orc_mod._VALID[bases]
+    dirty_want = ~vpad.reshape(n_words, 32).all(axis=1)
+    bits = np.unpackbits(pb.dirty.array[: (n_words + 31) // 32].view(np.uint8), bitorder="little")[:n_words]
+    assert (bits.astype(bool) == dirty_want).all()
+    assert pb.c.n_dirty == int(dirty_want.sum())
+    assert (pb.dirty_idx.array[: pb.c.n_dirty] == np.nonzero(dirty_want)[0]).all()
+
+
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")
+def test_pack_pool_concurrent_callers_and_fork(kmers):
+    """tb_pack_reads keeps persistent worker threads: two callers at once must both get correct
+    results (calls serialise), and a forked child (which inherits no workers) must still pack."""
+    import os
+    import threading
+
+    rng = np.random.default_rng(5)
+    n, L = 40, 20_000
+    offsets = np.arange(n + 1, dtype=np.int64) * L
+    batches = [np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n * L)].copy() for _ in range(2)]
+
+    def want(b):
+        return (orc_mod._CODE[b].reshape(-1, 32).astype(np.uint64) << (2 * np.arange(32, dtype=np.uint64))).sum(
+            axis=1, dtype=np.uint64)
+
+    pbs = [kmers.PackedBatch(n * L, n, pinned=False) for _ in range(2)]
+    errs = []
+
+    def run(i):
+        for _ in range(20):
+            pbs[i].pack(batches[i], offsets, 21, threads=4)
+            if not (pbs[i].F.array[: n * L // 32] == want(batches[i])).all():
+                errs.append(i)
+
+    ts = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+    pid = os.fork()
+    if pid == 0:
+        ok = 1
+        try:
+            pbs[0].pack(batches[1], offsets, 21, threads=3)
+            ok = 0 if (pbs[0].F.array[: n * L // 32] == want(batches[1])).all() else 2
+        finally:
+            os._exit(ok)
+    _, status = os.waitpid(pid, 0)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0

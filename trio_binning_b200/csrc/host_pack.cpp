@@ -15,8 +15,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -96,6 +101,54 @@ __attribute__((target("avx512f,avx512bw"))) inline void pack64_avx512(const unsi
     f1 = (uint64_t)_mm_extract_epi64(out, 1);
 }
 
+// The common case, a run of 256-base blocks with nothing but ACGT in them: 4 x 64 bytes in, one
+// 64-byte line of F out (non-temporal when F is line-aligned: the packed stream is read next by
+// the DMA engine, not by this core).  Validity and code both come from a 16-entry table indexed
+// by the low nibble of the byte ('A' 0x41, 'C' 0x43, 'T' 0x54, 'G' 0x47): the validity table
+// returns the full expected byte, so one compare against the input decides, and bytes >= 0x80
+// shuffle to 0 and fail it.  Stops in front of the first block that holds anything else and
+// returns the number of blocks done.  A core streams ~1.7x faster through this loop than through
+// one word at a time; the prefetch distance (4 KB) was picked by measurement.
+__attribute__((target("avx512f,avx512bw"))) int64_t pack_clean_blocks_avx512(const unsigned char *a,
+                                                                            int64_t n_blocks, uint64_t *F)
+{
+    const __m512i tv =
+        _mm512_broadcast_i32x4(_mm_setr_epi8(0, 'A', 0, 'C', 'T', 0, 0, 'G', 0, 0, 0, 0, 0, 0, 0, 0));
+    const __m512i tc = _mm512_broadcast_i32x4(_mm_setr_epi8(0, 0, 0, 1, 3, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0));
+    const __m512i m1 = _mm512_set1_epi16(0x0401), m2 = _mm512_set1_epi32(0x00100001);
+    const bool aligned = ((uintptr_t)F & 63) == 0;
+    int64_t b = 0;
+    for (; b < n_blocks; b++) {
+        const unsigned char *p = a + b * 256;
+        _mm_prefetch((const char *)p + 4096, _MM_HINT_T0);
+        _mm_prefetch((const char *)p + 4096 + 64, _MM_HINT_T0);
+        _mm_prefetch((const char *)p + 4096 + 128, _MM_HINT_T0);
+        _mm_prefetch((const char *)p + 4096 + 192, _MM_HINT_T0);
+        const __m512i x0 = _mm512_loadu_si512(p), x1 = _mm512_loadu_si512(p + 64);
+        const __m512i x2 = _mm512_loadu_si512(p + 128), x3 = _mm512_loadu_si512(p + 192);
+        const __mmask64 ok = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(tv, x0), x0) &
+                             _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(tv, x1), x1) &
+                             _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(tv, x2), x2) &
+                             _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(tv, x3), x3);
+        if (ok != ~0ull) break;
+        // 4 codes -> a byte: (c0 + 4 c1) per 16-bit lane, then (lo + 16 hi) per 32-bit lane
+        const __m512i c0 = _mm512_madd_epi16(_mm512_maddubs_epi16(_mm512_shuffle_epi8(tc, x0), m1), m2);
+        const __m512i c1 = _mm512_madd_epi16(_mm512_maddubs_epi16(_mm512_shuffle_epi8(tc, x1), m1), m2);
+        const __m512i c2 = _mm512_madd_epi16(_mm512_maddubs_epi16(_mm512_shuffle_epi8(tc, x2), m1), m2);
+        const __m512i c3 = _mm512_madd_epi16(_mm512_maddubs_epi16(_mm512_shuffle_epi8(tc, x3), m1), m2);
+        __m512i o = _mm512_castsi128_si512(_mm512_cvtepi32_epi8(c0));
+        o = _mm512_inserti32x4(o, _mm512_cvtepi32_epi8(c1), 1);
+        o = _mm512_inserti32x4(o, _mm512_cvtepi32_epi8(c2), 2);
+        o = _mm512_inserti32x4(o, _mm512_cvtepi32_epi8(c3), 3);
+        if (aligned)
+            _mm512_stream_si512((__m512i *)(F + b * 8), o);
+        else
+            _mm512_storeu_si512((void *)(F + b * 8), o);
+    }
+    _mm_sfence();
+    return b;
+}
+
 bool have_avx512()
 {
 #if defined(__x86_64__)
@@ -151,6 +204,16 @@ void pack_range(const unsigned char *ascii, int64_t total, const int64_t *offset
         uint64_t f;
         uint32_t valid;
 #if defined(__x86_64__)
+        if (avx512 && (w & 7) == 0) {
+            const int64_t n_blocks = std::min((w1 - w) / 8, (total - p0) / 256);
+            if (n_blocks > 0) {
+                const int64_t done = pack_clean_blocks_avx512(ascii + p0, n_blocks, F + w);
+                if (done > 0) {
+                    w += done * 8 - 1;  // the loop's w++ steps onto the first word not done
+                    continue;
+                }
+            }
+        }
         if (avx512 && w + 1 < w1 && p0 + 64 <= total) {
             // common case: two clean words at once
             uint64_t fa, fb, v64;
@@ -203,6 +266,69 @@ void pack_range(const unsigned char *ascii, int64_t total, const int64_t *offset
     }
 }
 
+// Persistent workers for tb_pack_reads: a batch is packed in 2-3 ms, and starting 15 threads per
+// call costs a tenth of that.  One job at a time (callers serialise on run_mutex); the caller
+// runs share 0 itself.  Heap-allocated and never destroyed, so no worker ever waits on a
+// destructed condition variable at exit; rebuilt in a forked child, which has no workers.
+class PackPool {
+  public:
+    static PackPool &get()
+    {
+        static std::mutex guard;
+        static PackPool *pool = nullptr;
+        static pid_t owner = 0;
+        std::lock_guard<std::mutex> lk(guard);
+        if (!pool || owner != getpid()) {
+            pool = new PackPool();
+            owner = getpid();
+        }
+        return *pool;
+    }
+
+    void run(int n, const std::function<void(int)> &f)
+    {
+        std::lock_guard<std::mutex> one(run_mutex_);
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            while ((int)workers_.size() < n - 1) {
+                workers_.emplace_back([this] { worker(); });
+                workers_.back().detach();
+            }
+            job_ = &f;
+            n_jobs_ = n;
+            next_ = 1;
+            pending_ = n - 1;
+        }
+        cv_work_.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return pending_ == 0; });
+        job_ = nullptr;
+        n_jobs_ = next_ = 0;
+    }
+
+  private:
+    void worker()
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            cv_work_.wait(lk, [&] { return next_ < n_jobs_; });
+            const int t = next_++;
+            const std::function<void(int)> *f = job_;
+            lk.unlock();
+            (*f)(t);
+            lk.lock();
+            if (--pending_ == 0) cv_done_.notify_one();
+        }
+    }
+
+    std::mutex run_mutex_, m_;
+    std::condition_variable cv_work_, cv_done_;
+    std::vector<std::thread> workers_;
+    const std::function<void(int)> *job_ = nullptr;
+    int n_jobs_ = 0, next_ = 0, pending_ = 0;
+};
+
 }  // namespace
 
 extern "C" {
@@ -232,19 +358,15 @@ int tb_pack_reads(const char *bases, const int64_t *offsets, int64_t n_reads, in
     if (threads < 1) threads = 1;
     std::vector<std::vector<DirtyWord>> dirty_lists((size_t)threads);
     std::vector<std::vector<int64_t>> ub_lists((size_t)threads);
-    auto work = [&](int t) {
+    const std::function<void(int)> work = [&](int t) {
         const int64_t t0 = tiles_total * t / threads, t1 = tiles_total * (t + 1) / threads;
         pack_range(ascii, total, offsets, n_reads, k, t0 * 32, t1 * 32, out->F, out->dirty,
                    dirty_lists[(size_t)t], ub_lists[(size_t)t]);
     };
-    if (threads == 1) {
+    if (threads == 1)
         work(0);
-    } else {
-        std::vector<std::thread> pool;
-        for (int t = 1; t < threads; t++) pool.emplace_back(work, t);
-        work(0);
-        for (auto &th : pool) th.join();
-    }
+    else
+        PackPool::get().run(threads, work);
 
     // merge the rare-path outputs (thread order == word order)
     for (auto &lst : dirty_lists) {
