@@ -12,12 +12,14 @@ its own replica of both sets; no collective on the data path).
 A "step" is one pass of the hot path over that batch.
   value  : bases/s with the batch already resident in HBM (pack + index + classify
            + fix-up + decide kernels; CUDA events on the launching stream)
-  e2e    : bases/s through the C-ABI classifier with PINNED HOST buffers -- H2D copy of
-           the ASCII bases + offsets and D2H copy of counts/scores/bins inside the
-           timed region, two slots in flight (double-buffered streams)
-  roofline: classify kernel only: (32 B x probes + 0.25 B x bases) / kernel time
-           against the measured HBM copy peak, plus the measured random-32-B-sector
-           gather ceiling of the same GPU.
+  e2e    : bases/s through the C-ABI classifier with ASCII reads in PINNED HOST buffers --
+           H2D copies and the D2H copy of counts/scores/bins inside the timed region,
+           one slot (stream) per batch in flight.  Three routes are timed and the best
+           is reported (e2e.route; all three in e2e_variants): ASCII over the link and
+           packed on the device, packed to 2 bits by the host cores first, and a mix of
+           the two that keeps the PCIe link and the host cores busy together.
+  roofline: classify kernel only, against the measured random-32-B-sector request
+           ceiling of the same GPU (tools/gather_sweep.py), with the HBM view beside it.
 Inputs and tables exceed the 126 MB L2 (config.l2); value_l2_flushed is the same
 measurement with L2 overwritten between the timed steps.
 """
@@ -310,7 +312,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     n_reads = wl["n_reads"]
     windows = synth.total_windows(offsets, k)
 
-    n_slots = 4  # two for the double-buffered routes, up to four for the hybrid cycle below
+    n_slots = 5  # two for the double-buffered routes, up to five for the hybrid cycle below
     clf = kmers.Classifier(A, B, max_bases=total, max_reads=n_reads, n_slots=n_slots)
     for slot in range(2):  # fill the pinned staging buffers once: these ARE the host inputs
         hb, ho = clf.staging(slot)
@@ -353,9 +355,9 @@ def run_gpu_arm(args, rank, local_rank, world):
     for pb in pbs:
         pb.pack(bases, offsets, k, threads=host_threads)
     t0 = time.perf_counter()
-    for _ in range(3):
+    for _ in range(10):
         pbs[0].pack(bases, offsets, k, threads=host_threads)
-    pack_s = (time.perf_counter() - t0) / 3
+    pack_s = (time.perf_counter() - t0) / 10
 
     def packed_pass(n_steps, pack_inside):
         clf.mark(0, 0)
@@ -402,7 +404,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     dist.barrier()
     e2e_hostpack_ms = dist.reduce(packed_pass(max(3, args.steps // 5), True), "MAX") * args.steps / max(3, args.steps // 5)
     # the mix of the two routes that balances link and host cores depends on the box: time
-    # 1 ASCII : 1, 2, 3 host-packed and keep the best (all are the same public calls)
+    # 1 ASCII : 1..4 host-packed and keep the best (all are the same public calls)
     hybrid = {}
     for n_packed in range(1, n_slots):
         cyc = 1 + n_packed
@@ -568,7 +570,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                            "api": "tb_classifier_submit_packed: 2-bit batches packed by tb_pack_reads, already in "
                                   "pinned host memory when the timed region starts (packing is reported in host_pack)"},
             "host_pack": {"value": total / pack_s, "unit": UNIT, "threads": host_threads,
-                          "what": "tb_pack_reads (AVX2, multi-threaded): ASCII -> 2-bit pinned batch, this rank"},
+                          "what": "tb_pack_reads (AVX-512/AVX2, multi-threaded): ASCII -> 2-bit pinned batch, this rank, mean of 10 calls"},
             "gpu_launches": 5 * args.steps,
             "value_l2_flushed": total_all / (flush_ms_max / args.steps * 1e-3),
             "roofline": roofline,
