@@ -34,4 +34,5 @@ print(f"filter=2^{fi['log2_bits']} pair={int(fi['pair_buckets']>0)} mini={int(fi
       f"reads={n_reads}x{mean_len} k={k} UNROLL={os.environ.get('TB_UNROLL','8')} TPB={os.environ.get('TB_TPB','128')} "
       f"L2G={os.environ.get('TB_L2_FETCH_GRANULARITY','32')}: step {ms/5:.3f} ms, classify {cls/5:.3f} ms, "
       f"{total/(cls/5*1e-3)/1e9:.2f} Gbases/s, {st['probes']/(cls/5*1e-3)/1e9:.2f} Gprobes/s "
-      f"(build {A.contents.build_ms:.0f}+{B.contents.build_ms:.0f} ms, setup {time.time()-t0:.0f}s)", flush=True)
+      f"(build {A.contents.build_ms:.0f}+{B.contents.build_ms:.0f} ms, setup {time.time()-t0:.0f}s) "
+      f"counts={int(ca.sum())}/{int(cb.sum())}", flush=True)

@@ -679,14 +679,16 @@ __device__ __forceinline__ KmerCoord coord_of_key(uint64_t key, int k, int m)
     return c;
 }
 
-// word index of a key's bitmap word: sector from the minimizer, word in the sector from the k-mer
-// (range reduction and the *8 + word go through IMAD.HI / IMAD: the FMA pipe is idle, the ALU
-// pipe is what bounds the kernel)
+// word index of a key's bitmap word: sector from the minimizer, word in the sector from the k-mer.
+// The minimum of several hashes is biased small; one odd multiply spreads it over the sectors
+// again (the range reduction takes the HIGH half of a product, which depends on every bit of
+// min_hash).  All of it runs as IMAD / IMAD.HI: the FMA pipe has room, the ALU pipe is what
+// bounds the kernel -- dropping a xor-shift here and taking the word from a product instead of
+// a shift+mask (4 ALU ops per window of 21) took the C2 kernel from 0.52 to 0.45 ms at the
+// same pass rate (profiles/r1_kernel_variants_alu.txt).
 __device__ __forceinline__ uint32_t mini_word_index(uint32_t min_hash, uint32_t fh, uint32_t n_sectors)
 {
-    uint32_t s = min_hash * 0xC2B2AE35u;  // the minimum of several hashes is biased small: re-spread
-    s ^= s >> 16;
-    return __umulhi(s, n_sectors) * 8u + ((fh >> 10) & 7u);
+    return __umulhi(min_hash * 0xC2B2AE35u, n_sectors) * 8u + __umulhi(fh * 0x9E3779B1u, 8u);
 }
 
 __device__ __forceinline__ uint32_t ld_filter_l1(const uint32_t *p, uint64_t policy)
@@ -698,6 +700,16 @@ __device__ __forceinline__ uint32_t ld_filter_l1(const uint32_t *p, uint64_t pol
     return v;
 }
 
+// Tuning notes for k_classify_pair_mini (all measured at C2, profiles/r1_kernel_variants_alu.txt):
+// the kernel sits between the ALU pipe (~17 ALU ops per window in phase 1) and load latency, and
+// ptxas' schedule decides which side wins -- fewer instructions is not always faster.  Kept:
+// product-based sector/word selection (0.52 -> 0.45 ms), 2 survivors per phase-2 round.
+// Measured and dropped: sliding minimum from shared 3- and 9-wide partial minima (1 op fewer
+// per window at k = 21, 5 fewer at k = 31, but 80 instead of 72 registers: 0.49 ms); bit
+// positions from the high bits of the hash without its last xor-shift (0.49 ms); m = 16 at
+// k = 21 (0.443 ms, but 14% more sector misses on sets beyond L2); a persistent tile loop with
+// the grid sized to the resident warps (0.51-0.56 ms: dynamic block scheduling balances
+// better); 7, 8 or 9 blocks per SM through launch bounds (0.51 / 0.53 / 0.81 ms).
 #ifndef TB_MINI_MIN_BLOCKS
 #define TB_MINI_MIN_BLOCKS 6
 #endif
@@ -727,10 +739,8 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
             // moved by 16 bases) keep the loop inside the instruction cache.
             constexpr uint32_t MMASK = MC == 16 ? 0xFFFFFFFFu : ((1u << (2 * MC)) - 1u);
             LaneCtx h = c;  // half-span view: window j of the half starts at base j of (f0,f1)
-            // m-mer hashes of the first WC-1 positions of a half; for short rings the second half
-            // inherits them from the first (its positions 16 .. 16+WC-2); for k = 31 (15 carried
-            // registers) recomputing them is cheaper than the spills
-            constexpr bool CARRY = WC <= 8;
+            // m-mer hashes of the first WC-1 positions of a half; the second half inherits them
+            // from the first (its positions 16 .. 16+WC-2)
             uint32_t head[WC > 1 ? WC - 1 : 1];
 #pragma unroll
             for (int q = 0; q < WC - 1; q++) {
@@ -741,17 +751,8 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
 #pragma unroll 1
             for (int half = 0; half < 2; half++) {
                 uint32_t hm[16 + WC];
-                if (CARRY || half == 0) {
 #pragma unroll
-                    for (int q = 0; q < WC - 1; q++) hm[q] = head[q];
-                } else {
-#pragma unroll
-                    for (int q = 0; q < WC - 1; q++) {
-                        const uint32_t f = (uint32_t)extract128(h.f0, h.f1, 2 * q) & MMASK;
-                        const uint32_t r = (uint32_t)extract128(h.r_lo, h.r_hi, 2 * (64 - q - MC)) & MMASK;
-                        hm[q] = mmer_mix(f < r ? f : r);
-                    }
-                }
+                for (int q = 0; q < WC - 1; q++) hm[q] = head[q];
                 uint32_t half_pass = 0;
 #pragma unroll
                 for (int g = 0; g < 16; g += U) {
@@ -779,10 +780,8 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
                         if ((need[u] & ~wd[u]) == 0) half_pass |= 1u << (g + u);
                 }
                 pass |= half_pass << (16 * half);
-                if (CARRY) {
 #pragma unroll
-                    for (int q = 0; q < WC - 1; q++) head[q] = hm[16 + q];
-                }
+                for (int q = 0; q < WC - 1; q++) head[q] = hm[16 + q];
                 // next half: drop 16 bases from the front of the span (and of its reverse complement)
                 h.f0 = (h.f0 >> 32) | (h.f1 << 32);
                 h.f1 >>= 32;
@@ -806,26 +805,28 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
         if (lane == 0 && np) atomicAdd(b.n_pass, (unsigned long long)np);
     }
 
-    // ---- phase 2 (as in k_classify_pair) ------------------------------------------------
+    // ---- phase 2 (as in k_classify_pair).  Two survivors per lane and round: with ~1% of the
+    // windows passing, most lanes hold none or one, and the whole warp pays for every slot
+    constexpr int P2 = 2;
     uint32_t hit_a = 0, hit_b = 0;
     uint32_t mm = pass;
     while (mm) {
-        int j[4];
-        uint64_t key[4];
-        uint32_t bkt[4];
-        tb_bucket bk[4];
+        int j[P2];
+        uint64_t key[P2];
+        uint32_t bkt[P2];
+        tb_bucket bk[P2];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < P2; q++) {
             j[q] = mm ? __ffs(mm) - 1 : -1;
             if (mm) mm &= mm - 1;
             key[q] = window_key<0>(c, j[q] < 0 ? 0 : j[q], k, kmask);
             bkt[q] = tb_pair_bucket_of(tb_hash64(key[q]), P.n_buckets);
         }
 #pragma unroll
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < P2; q++)
             if (j[q] >= 0) bk[q] = tb_load_bucket(P.table + bkt[q]);
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < P2; q++) {
             if (j[q] < 0) continue;
             uint32_t tags = tb_pair_tags(bk[q], key[q]);
             if (!tags && tb_pair_bucket_full(bk[q])) tags = tb_pair_overflow(P, key[q], bkt[q]);
