@@ -86,18 +86,56 @@ class Dist:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), sampled
+    in-process through NVML every 10 ms.  (A looping `nvidia-smi -lms 20` child was used first:
+    its queries cost the kernels under test ~6% while it ran -- `value` came out below the
+    L2-flushed figure that is taken after the sampler stops -- so it is only the fallback.)"""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    REASONS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
+        self.thread = None
+        self.sm, self.smax, self.reasons = [], [], set()
         self.path = os.path.join(tempfile.gettempdir(), f"tb_clocks_{os.getpid()}.csv")
+        self.mode = os.environ.get("TB_CLOCK_SAMPLER", "nvml")
+
+    def _nvml_loop(self, nv, handle):
+        try:
+            smax = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+        except Exception:
+            smax = None
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                if smax:
+                    self.smax.append(smax)
+                mask = int(get_reasons(handle)) if get_reasons else 0
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.010)
 
     def start(self):
+        if self.mode == "nvml":
+            try:
+                import pynvml as nv
+
+                nv.nvmlInit()
+                handle = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+                self._stop = threading.Event()
+                self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.thread = None
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
@@ -107,33 +145,39 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if not self.proc:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        self.f.close()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 9:
-                continue
+        out = {"sm_mhz": None, "sm_min_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "sampler": None}
+        if self.thread:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            out["sampler"] = "nvml thread, 10 ms"
+        elif self.proc:
+            self.proc.terminate()
             try:
-                sm.append(float(parts[1]))
-                smax.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)),
-                       reasons=sorted(reasons), samples=len(sm))
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.f.close()
+            out["sampler"] = "nvidia-smi -lms 20"
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    self.sm.append(float(parts[1]))
+                    self.smax.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"],
+                                     parts[3:7]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(name)
+            os.unlink(self.path)
+        else:
+            return out
+        if self.sm:
+            out.update(sm_mhz=float(np.median(self.sm)), sm_min_mhz=float(min(self.sm)),
+                       sm_max_mhz=float(max(self.smax)) if self.smax else None,
+                       reasons=sorted(self.reasons), samples=len(self.sm))
         return out
 
 
@@ -425,6 +469,8 @@ def run_gpu_arm(args, rank, local_rank, world):
     res_ms, cls_ms = clf.rerun_resident(0, args.steps)
     dist.barrier()
     clocks = sampler.stop()
+    quiet_ms, _ = clf.rerun_resident(0, args.steps)  # same measurement with the clock sampler off
+    quiet_ms_max = dist.reduce(quiet_ms, "MAX")
     # same, with a 512 MB buffer overwritten between the timed steps (cold L2 every step)
     flush_ms, flush_cls_ms = clf.rerun_resident(0, args.steps, flush_bytes=512 << 20)
     res_ms_max = dist.reduce(res_ms, "MAX")
@@ -573,6 +619,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                           "what": "tb_pack_reads (AVX-512/AVX2, multi-threaded): ASCII -> 2-bit pinned batch, this rank, mean of 10 calls"},
             "gpu_launches": 5 * args.steps,
             "value_l2_flushed": total_all / (flush_ms_max / args.steps * 1e-3),
+            "value_sampler_off": total_all / (quiet_ms_max / args.steps * 1e-3),
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,

@@ -14,7 +14,9 @@ KEEP = ['Kernel Name', 'Block Size', 'Grid Size', 'gpu__time_duration.sum', 'dra
         'sm__cycles_elapsed.max', 'smsp__thread_inst_executed_per_inst_executed.ratio',
         'l1tex__data_pipe_lsu_wavefronts_mem_lg.sum', 'l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed',
         'sm__inst_executed_pipe_lsu.sum', 'sm__inst_executed_pipe_alu.sum', 'sm__inst_executed_pipe_fma.sum',
-        'smsp__inst_executed_op_global_ld.sum']
+        'smsp__inst_executed_op_global_ld.sum', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'l1tex__t_sector_hit_rate.pct',
+        'sm__warps_active.avg.per_cycle_active']
 STALL = 'smsp__average_warps_issue_stalled_'
 
 
