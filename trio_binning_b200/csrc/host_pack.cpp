@@ -2,7 +2,7 @@
 //
 // north_star: "reads are parsed on the host ... into pinned, 2-bit-packed batches and
 // streamed with cudaMemcpyAsync".  This is that packer: the same arithmetic as the
-// device kernel k_pack (classify.cu), on the host, multi-threaded and AVX2-vectorised, so
+// device kernel k_pack (classify.cu), on the host, multi-threaded and AVX-512/AVX2-vectorised, so
 // that 0.25 byte per base crosses PCIe instead of 1.  It produces exactly the layout the
 // classify kernels consume (DESIGN.md "Data layout"):
 //   F       flat 2-bit forward stream (non-ACGT -> 0; reference c/kmers.c:56-68)

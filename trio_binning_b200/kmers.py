@@ -389,7 +389,7 @@ class PinnedBuffer:
 class PackedBatch:
     """Host-side 2-bit packed batch in pinned memory (tb_packed_batch) plus its packer.
 
-    `pack(bases, offsets, k)` runs the multi-threaded AVX2 host packer (host_pack.cpp);
+    `pack(bases, offsets, k)` runs the multi-threaded AVX-512/AVX2 host packer (host_pack.cpp);
     the arrays are then ready for `Classifier.submit_packed`."""
 
     def __init__(self, max_bases: int, max_reads: int, pinned: bool = True):
