@@ -80,6 +80,22 @@ def run(name):
         out["parity"] = {"method": "reverse-complement symmetry of all reads + planted haplotype wins",
                          "mismatches": int(((ra != ca) | (rb != cb)).sum())}
         assert out["parity"]["mismatches"] == 0
+    # phase-2 width: the other setting must give the same counts; record its kernel time
+    clf.close()
+    other = 4 if os.environ.get("TB_P2_WIDTH", "0") not in ("4",) else 2
+    prev = os.environ.get("TB_P2_WIDTH")
+    os.environ["TB_P2_WIDTH"] = str(other)
+    clf = kmers.Classifier(A, B, total, n_reads, 1)
+    clf.submit(0, bases, offsets)
+    wa, wb, *_ = clf.result(0)
+    assert (wa == ca).all() and (wb == cb).all(), "phase-2 width changed the counts"
+    clf.rerun_resident(0, 3)
+    _, cls_w = clf.rerun_resident(0, 10)
+    out[f"classify_ms_p2_width_{other}"] = cls_w / 10
+    if prev is None:
+        del os.environ["TB_P2_WIDTH"]
+    else:
+        os.environ["TB_P2_WIDTH"] = prev
     planted_a = float((bins[hap == 0] == 65).mean())
     planted_b = float((bins[hap == 1] == 66).mean())
     out["planted_called"] = [planted_a, planted_b]

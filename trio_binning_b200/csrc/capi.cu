@@ -331,6 +331,7 @@ struct tb_classifier {
     int filter_bits = 1;
     uint32_t filter_word_mask = 0;  // (bits / 32) - 1
     bool mini = false;              // bitmap sectors addressed by the key's minimizer
+    int p2_width = 2;               // table probes per lane and phase-2 round (minimizer kernel)
 };
 
 namespace {
@@ -400,7 +401,7 @@ int enqueue_kernels(tb_classifier *c, Slot &s, cudaEvent_t before_classify, cuda
     if (before_classify) CK(cudaEventRecord(before_classify, s.stream));
     if (c->d_pair && c->d_filter && c->mini) {
         tb_pair_view P = { c->d_pair, c->pair_buckets };
-        CK(tb_launch_classify_pair_mini(s.view, c->k, P, c->d_filter, (c->filter_word_mask >> 3) + 1, c->filter_bits, s.stream));
+        CK(tb_launch_classify_pair_mini(s.view, c->k, P, c->d_filter, (c->filter_word_mask >> 3) + 1, c->filter_bits, c->p2_width, s.stream));
     } else if (c->d_pair && c->d_filter) {
         tb_pair_view P = { c->d_pair, c->pair_buckets };
         CK(tb_launch_classify_pair(s.view, c->k, P, c->d_filter, c->filter_word_mask, c->filter_bits, s.stream));
@@ -426,6 +427,7 @@ int build_filter(tb_classifier *c)
     // minimizer-addressed sectors (default whenever the pair table exists): consecutive windows
     // share bitmap sectors, so the bitmap may be far larger than L2 and still cheap to read
     c->mini = pair_ok && env_int("TB_MINIMIZER", 1) != 0;
+    c->p2_width = env_int("TB_P2_WIDTH", 0) >= 4 ? 4 : 2;
     if (m < 0) {
         const uint64_t n = c->A->n_distinct + c->B->n_distinct;
         if (c->mini) {
@@ -888,7 +890,7 @@ int tb_classifier_submit_packed(tb_classifier *c, int slot, const tb_packed_batc
                               pb->n_ub, st));
     if (c->d_pair && c->d_filter && c->mini) {
         tb_pair_view P = { c->d_pair, c->pair_buckets };
-        CK(tb_launch_classify_pair_mini(v, c->k, P, c->d_filter, (c->filter_word_mask >> 3) + 1, c->filter_bits, st));
+        CK(tb_launch_classify_pair_mini(v, c->k, P, c->d_filter, (c->filter_word_mask >> 3) + 1, c->filter_bits, c->p2_width, st));
     } else if (c->d_pair && c->d_filter) {
         tb_pair_view P = { c->d_pair, c->pair_buckets };
         CK(tb_launch_classify_pair(v, c->k, P, c->d_filter, c->filter_word_mask, c->filter_bits, st));

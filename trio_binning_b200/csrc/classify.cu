@@ -713,7 +713,7 @@ __device__ __forceinline__ uint32_t ld_filter_l1(const uint32_t *p, uint64_t pol
 #ifndef TB_MINI_MIN_BLOCKS
 #define TB_MINI_MIN_BLOCKS 6
 #endif
-template <int K, int U, int NBITS>
+template <int K, int U, int NBITS, int P2>
 __global__ void __launch_bounds__(128, TB_MINI_MIN_BLOCKS)
 k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint32_t *__restrict__ filter,
                      uint32_t n_sectors)
@@ -805,9 +805,9 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
         if (lane == 0 && np) atomicAdd(b.n_pass, (unsigned long long)np);
     }
 
-    // ---- phase 2 (as in k_classify_pair).  Two survivors per lane and round: with ~1% of the
-    // windows passing, most lanes hold none or one, and the whole warp pays for every slot
-    constexpr int P2 = 2;
+    // ---- phase 2 (as in k_classify_pair).  P2 survivors per lane and round: the whole warp pays
+    // for every slot, so the launcher picks 2 where ~1% of the windows pass (most lanes hold none
+    // or one) and 4 where more do
     uint32_t hit_a = 0, hit_b = 0;
     uint32_t mm = pass;
     while (mm) {
@@ -970,16 +970,23 @@ cudaError_t launch_pair_k(const tb_batch_view &b, int k, tb_pair_view P, const u
 
 template <int K>
 cudaError_t launch_pair_mini_k(const tb_batch_view &b, int k, tb_pair_view P, const uint32_t *filter,
-                               uint32_t n_sectors, int n_bits, cudaStream_t stream)
+                               uint32_t n_sectors, int n_bits, int p2_width, cudaStream_t stream)
 {
     const int tpb = g_tpb;
     const int warps = tpb / 32;
     const unsigned blocks = (unsigned)((b.n_tiles + warps - 1) / warps);
     // 8 bitmap loads in flight per lane; 4 and 16 measured the same (profiles/r1_kernel_variants_minimizer*.txt)
-    if (n_bits == 2)
-        k_classify_pair_mini<K, 8, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors);
-    else
-        k_classify_pair_mini<K, 8, 1><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors);
+    if (n_bits == 2) {
+        if (p2_width >= 4)
+            k_classify_pair_mini<K, 8, 2, 4><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors);
+        else
+            k_classify_pair_mini<K, 8, 2, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors);
+    } else {
+        if (p2_width >= 4)
+            k_classify_pair_mini<K, 8, 1, 4><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors);
+        else
+            k_classify_pair_mini<K, 8, 1, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors);
+    }
     return cudaGetLastError();
 }
 
@@ -1061,13 +1068,13 @@ cudaError_t tb_launch_classify_pair(const tb_batch_view &b, int k, tb_pair_view 
 
 cudaError_t tb_launch_classify_pair_mini(const tb_batch_view &b, int k, tb_pair_view P,
                                          const uint32_t *filter, uint32_t n_sectors, int n_bits,
-                                         cudaStream_t stream)
+                                         int p2_width, cudaStream_t stream)
 {
     if (b.n_tiles == 0) return cudaSuccess;
     switch (k) {
-    case 21: return launch_pair_mini_k<21>(b, k, P, filter, n_sectors, n_bits, stream);
-    case 31: return launch_pair_mini_k<31>(b, k, P, filter, n_sectors, n_bits, stream);
-    default: return launch_pair_mini_k<0>(b, k, P, filter, n_sectors, n_bits, stream);
+    case 21: return launch_pair_mini_k<21>(b, k, P, filter, n_sectors, n_bits, p2_width, stream);
+    case 31: return launch_pair_mini_k<31>(b, k, P, filter, n_sectors, n_bits, p2_width, stream);
+    default: return launch_pair_mini_k<0>(b, k, P, filter, n_sectors, n_bits, p2_width, stream);
     }
 }
 

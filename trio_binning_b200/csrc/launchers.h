@@ -81,10 +81,11 @@ cudaError_t tb_launch_classify_pair(const tb_batch_view &b, int k, tb_pair_view 
                                     cudaStream_t stream);
 cudaError_t tb_launch_pair_filter_build(const uint64_t *d_pair_table, uint64_t n_slots, uint32_t *filter,
                                         uint32_t filter_word_mask, int n_bits, cudaStream_t stream);
-// minimizer-addressed variant for large sets: sector (8 words) chosen by the key's minimizer
+// minimizer-addressed variant for large sets: sector (8 words) chosen by the key's minimizer;
+// p2_width = table probes per lane and phase-2 round (2 or 4)
 cudaError_t tb_launch_classify_pair_mini(const tb_batch_view &b, int k, tb_pair_view P,
                                          const uint32_t *filter, uint32_t n_sectors, int n_bits,
-                                         cudaStream_t stream);
+                                         int p2_width, cudaStream_t stream);
 cudaError_t tb_launch_pair_filter_build_mini(const uint64_t *d_pair_table, uint64_t n_slots, uint32_t *filter,
                                              uint32_t n_sectors, int n_bits, int k, cudaStream_t stream);
 cudaError_t tb_launch_fixup(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
