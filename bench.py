@@ -64,10 +64,21 @@ class Dist:
             self.torch, self.dist = torch, dist
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29531")
-            dist.init_process_group(backend=backend)
             self.dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if backend == "nccl" else torch.device("cpu")
             if backend == "nccl":
                 torch.cuda.set_device(self.dev)
+            # NCCL prints its version banner on stdout when the first communicator is created;
+            # stdout carries exactly one JSON line, so send fd 1 to stderr until that is done
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group(backend=backend)
+                dist.barrier()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
 
     def barrier(self):
         if self.world > 1:
@@ -87,9 +98,9 @@ class Dist:
 
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), sampled
-    in-process through NVML every 10 ms.  (A looping `nvidia-smi -lms 20` child was used first:
-    its queries cost the kernels under test ~6% while it ran -- `value` came out below the
-    L2-flushed figure that is taken after the sampler stops -- so it is only the fallback.)"""
+    in-process through NVML every 10 ms (a looping `nvidia-smi -lms 20` child is the fallback;
+    `value_sampler_off` repeats the HBM-resident measurement after the sampler has stopped, as a
+    check that sampling does not disturb the kernels)."""
 
     REASONS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
     Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
