@@ -56,3 +56,60 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["unit"] == "bases/s" and line["value"] > 1e5
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def test_bench_reference_arm_under_torchrun_prints_one_line():
+    """N > 1: the driver launches the reference arm under torchrun; rank 0 alone works and prints
+    the line, the other ranks exit 0 silently."""
+    port = 29650 + os.getpid() % 200
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload",
+                        "c2_small", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [x for x in p.stdout.splitlines() if x.strip()]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2
+
+
+def _dist_stdout_worker(rank, world, port, queue):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    import bench
+
+    r, w = os.pipe()
+    saved = os.dup(1)
+    os.dup2(w, 1)  # capture fd 1 of this process
+    try:
+        d = bench.Dist(world, "gloo")
+        total = d.reduce(rank + 1, "SUM")
+        biggest = d.reduce(rank + 1, "MAX")
+        d.barrier()
+        if rank == 0:
+            print(json.dumps({"sum": total, "max": biggest}), flush=True)
+        d.close()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(w)
+    out = os.read(r, 1 << 16).decode() if rank == 0 else ""
+    queue.put((rank, out))
+
+
+def test_bench_dist_plumbing_gloo_world2():
+    """bench.py's torch.distributed plumbing (barrier, max/sum over ranks) on a world_size-2 gloo
+    group, and that bringing the group up leaves stdout to the one JSON line."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + os.getpid() % 100
+    procs = [ctx.Process(target=_dist_stdout_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = dict(q.get(timeout=120) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    lines = [x for x in got[0].splitlines() if x.strip()]
+    assert len(lines) == 1 and json.loads(lines[0]) == {"sum": 3.0, "max": 2.0}
