@@ -18,8 +18,11 @@ A "step" is one pass of the hot path over that batch.
            is reported (e2e.route; all three in e2e_variants): ASCII over the link and
            packed on the device, packed to 2 bits by the host cores first, and a mix of
            the two that keeps the PCIe link and the host cores busy together.
-  roofline: classify kernel only, against the measured random-32-B-sector request
-           ceiling of the same GPU (tools/gather_sweep.py), with the HBM view beside it.
+  roofline: classify kernel only, SURVEY 8(d)'s algorithmic bytes (32 B per window of the merged
+           table + 0.25 B per base) over the kernel time against the measured HBM copy peak, with
+           three explanatory views beside it: the bytes the kernel really needs from HBM, its
+           sector-request rate against the measured L2 random-sector ceiling, and the busiest
+           unit per ncu.
 Inputs and tables exceed the 126 MB L2 (config.l2); value_l2_flushed is the same
 measurement with L2 overwritten between the timed steps.
 """
