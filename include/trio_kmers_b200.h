@@ -200,6 +200,15 @@ int tb_float_repr(double x, char *buf, int buf_len);
 /* Parse a file with the native reader and write "name<TAB>seq<TAB>qual|<None>" per record
  * to out_fd (testing aid; no GPU involved).  Returns the number of records or < 0. */
 int64_t tb_fastx_dump(const char *reads_path, int out_fd);
+/* Decode a gzip file (or pass a non-gzip file through) with the pipeline's own streaming
+ * inflate, `chunk` bytes per read call, and write the result to out_fd (testing aid; no GPU
+ * involved).  Returns the number of bytes written, -1 cannot open, -2 corrupt input, -3 write
+ * error.  Replaces what the reference gets from Python's gzip module (seq.py:88-92). */
+int64_t tb_gunzip_fd(const char *path, int out_fd, int64_t chunk);
+/* The gzip CRC-32 the reader verifies members with (zlib crc32() semantics), and whether its
+ * carry-less-multiply path is active on this CPU (testing aids). */
+uint32_t tb_crc32(uint32_t crc, const void *buf, int64_t n);
+int tb_crc32_accelerated(void);
 
 /* Timing marks: record CUDA event `which` (0 or 1) on the slot's stream at the
  * current point of its queue; elapsed() waits for the `to` mark and returns the

@@ -17,12 +17,15 @@
 // the reference's plain mode depends on Python's buffered-writer behaviour (two handles on
 // one file, seq.py:129).
 #include <fcntl.h>
+#include <errno.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
 #include <zlib.h>
+
+#include "gz_stream.h"
 
 #include <algorithm>
 #include <charconv>
@@ -57,23 +60,28 @@ public:
         const size_t n = strlen(path);
         gz_ = n >= 3 && strcmp(path + n - 3, ".gz") == 0;  // seq.py:88: by file name only
         if (gz_) {
-            gzf_ = gzopen(path, "rb");
-            if (!gzf_) { err = std::string("cannot open ") + path; return false; }
-            gzbuffer(gzf_, 1 << 20);
+            if (!gzs_.open(path, err)) return false;
         } else {
             fd_ = ::open(path, O_RDONLY);
             if (fd_ < 0) { err = std::string("cannot open ") + path; return false; }
         }
-        buf_.resize(4 << 20);
+        for (auto &b : bufs_) b.data.resize(kBufBytes);
         return true;
     }
     ~LineSource()
     {
-        if (gzf_) gzclose(gzf_);
+        if (producer_.joinable()) {
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                stop_ = true;
+            }
+            cv_.notify_all();
+            producer_.join();
+        }
         if (fd_ >= 0) ::close(fd_);
     }
     // Next line into `line` INCLUDING its terminator translated to '\n' (absent only at
-    // end of input).  Returns false at end of input.
+    // end of input).  Returns false at end of input (or on a read error: see error()).
     bool next(std::string &line)
     {
         line.clear();
@@ -82,15 +90,17 @@ public:
             if (pending_cr_) {
                 // a '\r' ended the previous line; swallow the '\n' of a "\r\n" pair
                 pending_cr_ = false;
-                if (buf_[pos_] == '\n') {
+                if (cur_[pos_] == '\n') {
                     pos_++;
                     continue;
                 }
             }
-            const char *p = buf_.data() + pos_;
+            const char *p = cur_ + pos_;
             const size_t avail = len_ - pos_;
-            size_t i = 0;
-            while (i < avail && p[i] != '\n' && p[i] != '\r') i++;
+            // first '\n' or '\r' (two vectorised scans; '\r' is looked for only up to the '\n')
+            const char *nl = (const char *)memchr(p, '\n', avail);
+            size_t i = nl ? (size_t)(nl - p) : avail;
+            if (const char *cr = (const char *)memchr(p, '\r', i)) i = (size_t)(cr - p);
             line.append(p, i);
             pos_ += i;
             if (i < avail) {
@@ -101,32 +111,80 @@ public:
             }
         }
     }
-    uint64_t bytes_in() const { return bytes_in_; }
+    uint64_t bytes_in() const { return gz_ ? gzs_.compressed_bytes() : bytes_in_; }
+    const std::string &error() const { return error_; }
 
 private:
+    // Decompression (or the read syscalls) run ahead of the parser on their own thread, three
+    // 4 MB buffers going round: the line parser and the inflate each keep a core busy.
+    static constexpr size_t kBufBytes = 4u << 20;
+    struct Buf {
+        std::vector<char> data;
+        size_t len = 0;
+    };
+    void produce()
+    {
+        for (int k = 0;; k = (k + 1) % 3) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || n_ready_ < 3; });  // a buffer is free again
+                if (stop_) return;
+            }
+            Buf &b = bufs_[k];
+            long got;
+            if (gz_) {
+                got = gzs_.read(b.data.data(), b.data.size());
+            } else {
+                do got = (long)::read(fd_, b.data.data(), b.data.size());
+                while (got < 0 && errno == EINTR);
+                if (got > 0) bytes_in_ += (uint64_t)got;
+            }
+            std::lock_guard<std::mutex> lk(m_);
+            if (got < 0) error_ = gz_ ? ("corrupt gzip input: " + gzs_.error()) : std::string("read error on the reads file");
+            b.len = got > 0 ? (size_t)got : 0;
+            n_ready_++;
+            cv_.notify_all();
+            if (got <= 0) return;  // an empty buffer tells the parser that the input is over
+        }
+    }
     bool fill()
     {
         if (eof_) return false;
-        long got;
-        if (gz_)
-            got = gzread(gzf_, buf_.data(), (unsigned)buf_.size());
-        else
-            got = (long)::read(fd_, buf_.data(), buf_.size());
-        if (got <= 0) {
+        if (!producer_.joinable()) producer_ = std::thread([this] { produce(); });
+        std::unique_lock<std::mutex> lk(m_);
+        if (have_cur_) {  // hand the consumed buffer back
+            have_cur_ = false;
+            n_ready_--;
+            cv_.notify_all();
+        }
+        cv_.wait(lk, [&] { return n_ready_ > 0; });
+        Buf &b = bufs_[next_];
+        next_ = (next_ + 1) % 3;
+        if (b.len == 0) {
             eof_ = true;
+            n_ready_--;
             return false;
         }
-        bytes_in_ += (uint64_t)got;
+        have_cur_ = true;
+        cur_ = b.data.data();
         pos_ = 0;
-        len_ = (size_t)got;
+        len_ = b.len;
         return true;
     }
     bool gz_ = false, eof_ = false, pending_cr_ = false;
-    gzFile gzf_ = nullptr;
+    tb::GzStream gzs_;
     int fd_ = -1;
-    std::vector<char> buf_;
+    Buf bufs_[3];
+    std::thread producer_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    int n_ready_ = 0;   // buffers filled and not yet handed back (incl. the parser's current one)
+    int next_ = 0;      // next buffer the parser takes
+    bool have_cur_ = false, stop_ = false;
+    const char *cur_ = nullptr;
     size_t pos_ = 0, len_ = 0;
     uint64_t bytes_in_ = 0;
+    std::string error_;
 };
 
 // number of characters (code points) in a UTF-8 byte string: Python counts characters
@@ -370,6 +428,7 @@ struct Reader {
                 break;
             }
         }
+        if (!src.error().empty() && error.empty()) error = src.error();  // never a silently short result
         cur->last = true;
         full_q->push(cur);
         seconds = seconds_since(t0);

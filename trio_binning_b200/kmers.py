@@ -180,6 +180,11 @@ lib.tb_classify_fastx.argtypes = [C.c_char_p, HashSet, HashSet, C.c_char_p, C.c_
 lib.tb_float_repr.argtypes = [C.c_double, C.c_char_p, C.c_int]
 lib.tb_fastx_dump.argtypes = [C.c_char_p, C.c_int]
 lib.tb_fastx_dump.restype = C.c_int64
+lib.tb_gunzip_fd.argtypes = [C.c_char_p, C.c_int, C.c_int64]
+lib.tb_gunzip_fd.restype = C.c_int64
+lib.tb_crc32.argtypes = [C.c_uint32, C.c_char_p, C.c_int64]
+lib.tb_crc32.restype = C.c_uint32
+lib.tb_crc32_accelerated.restype = C.c_int
 
 
 def _error() -> str:
@@ -616,6 +621,33 @@ def fastx_dump(reads_path: str):
         out.append((name, seq, None if qual == b"<None>" else qual))
     assert len(out) == n
     return out
+
+
+def gunzip(path: str, chunk: int = 0) -> bytes:
+    """Contents of a .gz file (or of a non-gzip file, passed through) as decoded by the native
+    reader's own streaming inflate, read `chunk` bytes at a time (testing aid, no GPU needed).
+    Raises ValueError for corrupt or truncated input."""
+    import tempfile
+
+    with tempfile.TemporaryFile() as tmp:
+        n = lib.tb_gunzip_fd(os.fsencode(path), tmp.fileno(), chunk)
+        if n == -2:
+            raise ValueError(f"{path}: corrupt or truncated gzip data")
+        if n < 0:
+            raise OSError(f"tb_gunzip_fd({path}) failed ({n})")
+        tmp.seek(0)
+        data = tmp.read()
+    assert len(data) == n
+    return data
+
+
+def crc32(data: bytes, crc: int = 0) -> int:
+    """gzip CRC-32 as computed by the native reader (zlib.crc32 semantics; testing aid)."""
+    return int(lib.tb_crc32(crc & 0xFFFFFFFF, data, len(data)))
+
+
+def crc32_accelerated() -> bool:
+    return bool(lib.tb_crc32_accelerated())
 
 
 def gather_bench(table_bytes: int, loads_in_flight: int = 8, threads_per_block: int = 256,
