@@ -1,5 +1,6 @@
 """End-to-end CLI timing on a synthetic FASTQ(.gz): native pipeline vs Python I/O
-(run on the GPU box).  usage: pipeline_bench.py [n_reads] [mean_len]"""
+(run on the GPU box).  usage: pipeline_bench.py [n_reads] [mean_len] [only] [n_keys]
+`only`: comma-separated substrings of the run labels to keep (default: all five runs)"""
 import gzip
 import io
 import os
@@ -16,9 +17,11 @@ from trio_binning_b200 import synth  # noqa: E402
 
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 mean_len = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
+only = [x for x in (sys.argv[3].split(",") if len(sys.argv) > 3 else []) if x]
+n_keys = int(sys.argv[4]) if len(sys.argv) > 4 else 10_000_000
 k = 21
 tmp = tempfile.mkdtemp(prefix="tb_pipe_")
-ka, kb, pa, pb = synth.materialise_sets(tmp, 10_000_000, 10_000_000, k, seed=42)
+ka, kb, pa, pb = synth.materialise_sets(tmp, n_keys, n_keys, k, seed=42)
 bases, offsets, _ = synth.random_reads(n_reads, mean_len, k, ka, kb, seed=43, plant_every=1000)
 rng = np.random.default_rng(1)
 t0 = time.time()
@@ -33,11 +36,13 @@ subprocess.run(f"gzip -1 -k -f {path_plain}", shell=True, check=True)
 total = int(offsets[-1])
 print(f"input: {n_reads} reads, {total/1e6:.0f} Mbases, fastq {os.path.getsize(path_plain)/1e6:.0f} MB, "
       f"gz {os.path.getsize(path_gz)/1e6:.0f} MB (made in {time.time()-t0:.0f}s)", flush=True)
-for label, reads, extra in (("native gz-in level9", path_gz, []),
+for label, reads, extra in (("native gz-in level9", path_gz, ["--gzip-level", "9"]),
                             ("native gz-in level6", path_gz, ["--gzip-level", "6"]),
                             ("native gz-in level1", path_gz, ["--gzip-level", "1"]),
                             ("native plain-in level1", path_plain, ["--gzip-level", "1"]),
                             ("python-io gz-in", path_gz, ["--python-io"])):
+    if only and not any(x in label for x in only):
+        continue
     out = os.path.join(tmp, label.replace(" ", "_"))
     os.makedirs(out, exist_ok=True)
     cmd = [sys.executable, "-m", "trio_binning_b200.classify_by_kmers", reads, pa, pb,
