@@ -198,7 +198,8 @@ int tb_classify_fastx(const char *reads_path, const hash_set *A, const hash_set 
 /* Python's repr(float) of x into buf (testing aid for the TSV writer). */
 int tb_float_repr(double x, char *buf, int buf_len);
 /* Parse a file with the native reader and write "name<TAB>seq<TAB>qual|<None>" per record
- * to out_fd (testing aid; no GPU involved).  Returns the number of records or < 0. */
+ * to out_fd (testing aid; no GPU involved).  Returns the number of records, or < 0: -1 cannot
+ * open, -2 unreadable input (corrupt gzip data; message in tb_last_error), -3 out of memory. */
 int64_t tb_fastx_dump(const char *reads_path, int out_fd);
 /* Decode a gzip file (or pass a non-gzip file through) with the pipeline's own streaming
  * inflate, `chunk` bytes per read call, and write the result to out_fd (testing aid; no GPU

@@ -34,7 +34,7 @@ def _check(kmers, tmp_path, blob, want, name="x.gz", chunks=(0, 1 << 20, 4093, 7
 
 def _corpus():
     rng = np.random.default_rng(11)
-    fastq = b"".join(b"@r%d desc\n" % i + bytes(rng.choice(list(b"ACGT"), 300)) + b"\n+\n" +
+    fastq = b"".join(b"@r%d desc\n" % i + rng.choice(list(b"ACGT"), 300).astype(np.uint8).tobytes() + b"\n+\n" +
                      bytes(rng.integers(33, 74, 300, dtype=np.uint8)) + b"\n" for i in range(400))
     period = bytes(rng.integers(0, 256, 32768, dtype=np.uint8))
     return {
@@ -47,7 +47,7 @@ def _corpus():
         "run_lengths": b"".join(bytes([i % 251]) * (i % 700 + 1) for i in range(3000)),
         "period_32768": period * 40,           # matches at the maximum distance, across window slides
         "period_32767_plus": (period[:-1]) * 40 + b"tail",
-        "two_symbols": bytes(rng.choice([65, 67], 200_000)),
+        "two_symbols": rng.choice([65, 67], 200_000).astype(np.uint8).tobytes(),
         "big_mixed": fastq * 30 + bytes(rng.integers(0, 256, 3_000_000, dtype=np.uint8)) + fastq * 30,
     }
 

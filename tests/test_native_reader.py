@@ -95,3 +95,25 @@ def test_float_repr_matches_python(kmers):
     values += [rng.random() * 10 ** rng.randrange(-30, 30) for _ in range(3000)]
     for v in values:
         assert kmers.float_repr(v) == repr(float(v)), v
+
+
+def test_corrupt_gzip_input_is_an_error_not_a_short_result(tmp_path):
+    """The reference reads through Python's gzip module, which raises on damaged files; the native
+    reader must not hand back the records it managed to parse as if the file had ended there."""
+    import numpy as np
+
+    from trio_binning_b200 import kmers
+
+    rng = np.random.default_rng(9)
+    text = b"".join(b"@r%d\n" % i + rng.choice(list(b"ACGT"), 500).astype(np.uint8).tobytes() + b"\n+\n" + b"I" * 500 + b"\n"
+                    for i in range(300))
+    good = tmp_path / "ok.fastq.gz"
+    good.write_bytes(gzip.compress(text))
+    assert len(kmers.fastx_dump(str(good))) == 300
+    blob = bytearray(good.read_bytes())
+    for name, damaged in (("cut", blob[: len(blob) // 2]), ("flip", blob[:4000] + bytes([blob[4000] ^ 0xFF]) + blob[4001:]),
+                          ("no_trailer", blob[:-8])):
+        p = tmp_path / f"{name}.fastq.gz"
+        p.write_bytes(bytes(damaged))
+        with pytest.raises(RuntimeError, match="gzip"):
+            kmers.fastx_dump(str(p))

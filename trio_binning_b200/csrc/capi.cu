@@ -500,6 +500,8 @@ tb_classifier *g_default = nullptr;
 extern "C" {
 
 const char *tb_last_error(void) { return g_err.c_str(); }
+// for the other translation units of the library (not part of the public header)
+void tb_internal_set_error(const char *message) { g_err = message ? message : ""; }
 const char *tb_version(void) { return "trio_kmers_b200 0.1 (sm_100a)"; }
 
 int tb_device_count(void)

@@ -42,6 +42,8 @@
 
 #include "../../include/trio_kmers_b200.h"
 
+extern "C" void tb_internal_set_error(const char *message);  // capi.cu
+
 namespace {
 
 using Clock = std::chrono::steady_clock;
@@ -792,6 +794,7 @@ int tb_classify_fastx(const char *reads_path, const hash_set *A, const hash_set 
     if (clf) tb_classifier_destroy(clf);
     if (!reader.error.empty()) {
         fprintf(stderr, "tb_classify_fastx: %s\n", reader.error.c_str());
+        if (!rc) tb_internal_set_error(reader.error.c_str());
         rc = rc ? rc : -10;
     }
     if (stats) {
@@ -869,6 +872,10 @@ int64_t tb_fastx_dump(const char *reads_path, int out_fd)
         if (last) break;
     }
     t.join();
+    if (!reader.error.empty()) {
+        tb_internal_set_error(reader.error.c_str());
+        return -2;
+    }
     return n;
 }
 

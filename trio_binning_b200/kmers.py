@@ -612,7 +612,7 @@ def fastx_dump(reads_path: str):
     with tempfile.TemporaryFile() as tmp:
         n = lib.tb_fastx_dump(os.fsencode(reads_path), tmp.fileno())
         if n < 0:
-            raise RuntimeError(f"tb_fastx_dump failed ({n})")
+            raise RuntimeError(f"tb_fastx_dump failed ({n}): {_error()}")
         tmp.seek(0)
         data = tmp.read()
     out = []
