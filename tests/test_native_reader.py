@@ -117,3 +117,71 @@ def test_corrupt_gzip_input_is_an_error_not_a_short_result(tmp_path):
         p.write_bytes(bytes(damaged))
         with pytest.raises(RuntimeError, match="gzip"):
             kmers.fastx_dump(str(p))
+
+
+def _bgzf(data, block=65280, level=6, eof_marker=True):
+    """bgzip's container (SAM spec 4.1): independent gzip members of <= 64 KB, each with a 'BC'
+    extra subfield holding its total size - 1."""
+    import struct
+    import zlib
+
+    out = bytearray()
+    pieces = [data[i:i + block] for i in range(0, len(data), block)] + ([b""] if eof_marker else [])
+    for piece in pieces:
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        raw = c.compress(piece) + c.flush()
+        total = 12 + 6 + len(raw) + 8
+        out += bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff]) + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, total - 1)
+        out += raw + struct.pack("<II", zlib.crc32(piece), len(piece))
+    return bytes(out)
+
+
+def _fastq_text(n, length, seed):
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    recs, parts = [], []
+    for i in range(n):
+        s = rng.choice(list(b"ACGT"), length).astype(np.uint8).tobytes()
+        q = rng.integers(33, 74, length, dtype=np.uint8).tobytes()
+        recs.append((b"r%d" % i, s, q))
+        parts.append(b"@r%d some comment\n" % i + s + b"\n+\n" + q + b"\n")
+    return recs, b"".join(parts)
+
+
+def test_bgzf_input_is_decoded_in_parallel_and_in_order(tmp_path):
+    """BGZF (bgzip) input: groups of blocks are inflated by worker threads and must come out in
+    stream order, records spanning block and task boundaries intact."""
+    import gzip
+
+    from trio_binning_b200 import kmers
+
+    recs, text = _fastq_text(700, 3000, 21)  # ~4.2 MB: several 512 KB tasks
+    for name, blob in (("bgzf.fastq.gz", _bgzf(text)), ("bgzf_small_blocks.fastq.gz", _bgzf(text, block=777, level=1)),
+                       ("bgzf_no_eof.fastq.gz", _bgzf(text, eof_marker=False)),
+                       ("bgzf_then_gzip.fastq.gz", _bgzf(text[:2_000_003], eof_marker=False) + gzip.compress(text[2_000_003:])),
+                       ("gzip_then_bgzf.fastq.gz", gzip.compress(text[:1_000_001]) + _bgzf(text[1_000_001:])),
+                       ("bgzf_padded.fastq.gz", _bgzf(text) + bytes(37))):
+        p = tmp_path / name
+        p.write_bytes(blob)
+        assert gzip.decompress(blob) == text  # (Python's gzip tolerates zero padding after the last member)
+        got = kmers.fastx_dump(str(p))
+        assert got == recs, name
+        assert kmers.gunzip(str(p)) == text  # the serial decoder reads the same container
+
+
+def test_bgzf_damage_is_an_error(tmp_path):
+    from trio_binning_b200 import kmers
+
+    _, text = _fastq_text(300, 3000, 22)
+    blob = bytearray(_bgzf(text))
+    cases = {
+        "flip_payload": lambda b: b[:200_000] + bytes([b[200_000] ^ 0x40]) + b[200_001:],
+        "cut_mid_block": lambda b: b[: len(b) // 2],
+        "wrong_isize": lambda b: b[:-28 - 1] + bytes([b[-28 - 1] ^ 1]) + b[-28:],
+    }
+    for name, fn in cases.items():
+        p = tmp_path / f"{name}.fastq.gz"
+        p.write_bytes(bytes(fn(blob)))
+        with pytest.raises(RuntimeError, match="gzip"):
+            kmers.fastx_dump(str(p))

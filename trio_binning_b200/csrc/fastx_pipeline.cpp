@@ -57,29 +57,31 @@ double seconds_since(Clock::time_point t0)
 // ---------------------------------------------------------------------------------------
 class LineSource {
 public:
+    // host threads that may decode in parallel (BGZF input only); call before the first next()
+    void set_threads(int n) { decode_threads_ = n < 1 ? 1 : (n > 8 ? 8 : n); }
     bool open(const char *path, std::string &err)
     {
         const size_t n = strlen(path);
         gz_ = n >= 3 && strcmp(path + n - 3, ".gz") == 0;  // seq.py:88: by file name only
+        fd_ = ::open(path, O_RDONLY);
+        if (fd_ < 0) { err = std::string("cannot open ") + path; return false; }
         if (gz_) {
-            if (!gzs_.open(path, err)) return false;
-        } else {
-            fd_ = ::open(path, O_RDONLY);
-            if (fd_ < 0) { err = std::string("cannot open ") + path; return false; }
+            unsigned char head[64];
+            const ssize_t got = ::pread(fd_, head, sizeof head, 0);
+            size_t total = 0;
+            bgzf_ = got >= 18 && bgzf_block_size(head, (size_t)got, total);
         }
-        for (auto &b : bufs_) b.data.resize(kBufBytes);
         return true;
     }
     ~LineSource()
     {
-        if (producer_.joinable()) {
-            {
-                std::lock_guard<std::mutex> lk(m_);
-                stop_ = true;
-            }
-            cv_.notify_all();
-            producer_.join();
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
         }
+        cv_.notify_all();
+        if (producer_.joinable()) producer_.join();
+        for (auto &w : workers_) w.join();
         if (fd_ >= 0) ::close(fd_);
     }
     // Next line into `line` INCLUDING its terminator translated to '\n' (absent only at
@@ -113,79 +115,272 @@ public:
             }
         }
     }
-    uint64_t bytes_in() const { return gz_ ? gzs_.compressed_bytes() : bytes_in_; }
+    uint64_t bytes_in() const { return bytes_in_; }
     const std::string &error() const { return error_; }
+    bool parallel_bgzf() const { return bgzf_ && decode_threads_ > 1; }
 
 private:
-    // Decompression (or the read syscalls) run ahead of the parser on their own thread, three
-    // 4 MB buffers going round: the line parser and the inflate each keep a core busy.
-    static constexpr size_t kBufBytes = 4u << 20;
-    struct Buf {
+    // Decompression (or the read syscalls) run ahead of the parser: a producer thread hands
+    // over chunks of decoded text in stream order.  Plain gzip is one serial stream (GzStream
+    // on the producer thread).  BGZF input (bgzip, htslib: independent <= 64 KB gzip members
+    // that carry their compressed size in a 'BC' extra field) is cut into groups of blocks that
+    // worker threads decode side by side; anything that stops looking like BGZF is handed to the
+    // serial decoder from that offset on.
+    static constexpr size_t kChunkBytes = 4u << 20;
+    static constexpr size_t kTaskBytes = 512u << 10;  // compressed bytes per BGZF task
+    struct Chunk {
         std::vector<char> data;
         size_t len = 0;
+        bool done = false, failed = false;
+        std::vector<unsigned char> comp;  // BGZF task: the compressed blocks
+        size_t expect = 0;                //            and the sum of their ISIZE fields
+        std::string why;
     };
-    void produce()
+    using ChunkPtr = std::shared_ptr<Chunk>;
+
+    // size of the BGZF block starting at p, if it is one (SAM spec 4.1: FEXTRA with a BC subfield)
+    static bool bgzf_block_size(const unsigned char *p, size_t n, size_t &total)
     {
-        for (int k = 0;; k = (k + 1) % 3) {
-            {
-                std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [&] { return stop_ || n_ready_ < 3; });  // a buffer is free again
-                if (stop_) return;
+        if (n < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return false;
+        const size_t xlen = p[10] | ((size_t)p[11] << 8);
+        if (n < 12 + xlen) return false;
+        for (size_t q = 12; q + 4 <= 12 + xlen;) {
+            const size_t slen = p[q + 2] | ((size_t)p[q + 3] << 8);
+            if (p[q] == 'B' && p[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen) {
+                total = (size_t)(p[q + 4] | (p[q + 5] << 8)) + 1;
+                return total >= 12 + xlen + 8 + 2;
             }
-            Buf &b = bufs_[k];
+            q += 4 + slen;
+        }
+        return false;
+    }
+
+    ChunkPtr fresh_chunk()
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        if (!free_.empty()) {
+            ChunkPtr c = free_.back();
+            free_.pop_back();
+            c->len = c->expect = 0;
+            c->done = c->failed = false;
+            c->comp.clear();
+            c->why.clear();
+            return c;
+        }
+        return std::make_shared<Chunk>();
+    }
+    // append to the ordered queue (blocks while too many chunks are in flight); false = stopping
+    bool enqueue(const ChunkPtr &c, bool as_work)
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return stop_ || ordered_.size() < max_in_flight_; });
+        if (stop_) return false;
+        ordered_.push_back(c);
+        if (as_work) work_.push_back(c);
+        cv_.notify_all();
+        return true;
+    }
+    void finish(const ChunkPtr &c)
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        c->done = true;
+        cv_.notify_all();
+    }
+    void push_end(bool failed, const std::string &why)
+    {
+        ChunkPtr c = fresh_chunk();
+        c->failed = failed;
+        c->why = why;
+        c->done = true;
+        enqueue(c, false);
+    }
+
+    // serial stream: the producer thread decodes (or reads) chunk after chunk
+    void produce_serial(bool continue_on_fd)
+    {
+        if (gz_) {
+            gzs_.open_fd(fd_, !continue_on_fd);
+        }
+        for (;;) {
+            ChunkPtr c = fresh_chunk();
+            c->data.resize(kChunkBytes);
             long got;
             if (gz_) {
-                got = gzs_.read(b.data.data(), b.data.size());
+                got = gzs_.read(c->data.data(), c->data.size());
+                bytes_in_ = bgzf_bytes_ + gzs_.compressed_bytes();
             } else {
-                do got = (long)::read(fd_, b.data.data(), b.data.size());
+                do got = (long)::read(fd_, c->data.data(), c->data.size());
                 while (got < 0 && errno == EINTR);
                 if (got > 0) bytes_in_ += (uint64_t)got;
             }
-            std::lock_guard<std::mutex> lk(m_);
-            if (got < 0) error_ = gz_ ? ("corrupt gzip input: " + gzs_.error()) : std::string("read error on the reads file");
-            b.len = got > 0 ? (size_t)got : 0;
-            n_ready_++;
-            cv_.notify_all();
-            if (got <= 0) return;  // an empty buffer tells the parser that the input is over
+            if (got <= 0) {
+                push_end(got < 0, gz_ ? ("corrupt gzip input: " + gzs_.error()) : std::string("read error on the reads file"));
+                return;
+            }
+            c->len = (size_t)got;
+            c->done = true;
+            if (!enqueue(c, false)) return;
         }
     }
+
+    // BGZF: walk the block headers, hand groups of whole blocks to the workers
+    void produce_bgzf()
+    {
+        std::vector<unsigned char> buf(8u << 20);
+        size_t have = 0;
+        uint64_t off = 0;  // file offset of buf[0]
+        bool eof = false;
+        for (;;) {
+            while (!eof && have < buf.size()) {
+                const ssize_t n = ::pread(fd_, buf.data() + have, buf.size() - have, (off_t)(off + have));
+                if (n < 0) {
+                    if (errno == EINTR) continue;
+                    push_end(true, "read error on the reads file");
+                    return;
+                }
+                if (n == 0) eof = true;
+                have += (size_t)n;
+            }
+            size_t p = 0;
+            bool not_bgzf = false;
+            ChunkPtr task = fresh_chunk();
+            for (;;) {
+                size_t total = 0;
+                if (have - p < 18) break;
+                if (!bgzf_block_size(buf.data() + p, have - p, total)) {
+                    not_bgzf = true;
+                    break;
+                }
+                if (have - p < total) break;
+                const unsigned char *t = buf.data() + p + total - 4;
+                task->comp.insert(task->comp.end(), buf.data() + p, buf.data() + p + total);
+                task->expect += (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
+                p += total;
+                if (task->comp.size() >= kTaskBytes) {
+                    if (!enqueue(task, true)) return;
+                    task = fresh_chunk();
+                }
+            }
+            if (!task->comp.empty() && !enqueue(task, true)) return;
+            memmove(buf.data(), buf.data() + p, have - p);
+            have -= p;
+            off += p;
+            bgzf_bytes_ = off;
+            bytes_in_ = off;
+            if (not_bgzf || (eof && have > 0) || (have == buf.size())) {
+                // not (or no longer) BGZF, or a partial block at the end: the serial decoder
+                // takes over from here and decides what it is (member, garbage, truncation)
+                if (::lseek(fd_, (off_t)off, SEEK_SET) < 0) {
+                    push_end(true, "cannot seek in the reads file");
+                    return;
+                }
+                produce_serial(true);
+                return;
+            }
+            if (eof) {
+                push_end(false, "");
+                return;
+            }
+        }
+    }
+
+    void work()
+    {
+        tb::GzStream gz;  // one decoder per worker, re-opened on every task
+        for (;;) {
+            ChunkPtr c;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || !work_.empty(); });
+                if (stop_) return;
+                c = work_.front();
+                work_.pop_front();
+            }
+            c->data.resize(c->expect ? c->expect : 1);
+            gz.open_memory(c->comp.data(), c->comp.size());
+            size_t n = 0;
+            bool bad = false;
+            for (;;) {
+                // one spare byte of room shows an overlong stream instead of truncating it
+                char extra;
+                const long got = n < c->expect ? gz.read(c->data.data() + n, c->expect - n) : gz.read(&extra, 1);
+                if (got < 0) { bad = true; c->why = "corrupt gzip input: " + gz.error(); break; }
+                if (got == 0) break;
+                if (n >= c->expect) { bad = true; c->why = "corrupt gzip input: BGZF block longer than its ISIZE"; break; }
+                n += (size_t)got;
+            }
+            if (!bad && n != c->expect) {
+                bad = true;
+                c->why = "corrupt gzip input: BGZF block shorter than its ISIZE";
+            }
+            c->len = n;
+            c->failed = bad;
+            finish(c);
+        }
+    }
+
+    void start()
+    {
+        started_ = true;
+        if (parallel_bgzf()) {
+            max_in_flight_ = 2 + 2 * (size_t)decode_threads_;
+            for (int i = 0; i < decode_threads_; i++) workers_.emplace_back([this] { work(); });
+            producer_ = std::thread([this] { produce_bgzf(); });
+        } else {
+            producer_ = std::thread([this] { produce_serial(false); });
+        }
+    }
+
     bool fill()
     {
         if (eof_) return false;
-        if (!producer_.joinable()) producer_ = std::thread([this] { produce(); });
+        if (!started_) start();
         std::unique_lock<std::mutex> lk(m_);
-        if (have_cur_) {  // hand the consumed buffer back
-            have_cur_ = false;
-            n_ready_--;
+        if (cur_chunk_) {  // hand the consumed chunk back
+            free_.push_back(cur_chunk_);
+            cur_chunk_.reset();
+        }
+        for (;;) {
+            cv_.wait(lk, [&] { return !ordered_.empty() && ordered_.front()->done; });
+            ChunkPtr c = ordered_.front();
+            ordered_.pop_front();
             cv_.notify_all();
+            if (c->failed) {
+                error_ = c->why;
+                eof_ = true;
+                return false;
+            }
+            if (c->len == 0) {
+                if (c->comp.empty()) {  // the end marker
+                    eof_ = true;
+                    return false;
+                }
+                free_.push_back(c);  // a task of empty blocks (BGZF end-of-file marker): next
+                continue;
+            }
+            cur_chunk_ = c;
+            cur_ = c->data.data();
+            pos_ = 0;
+            len_ = c->len;
+            return true;
         }
-        cv_.wait(lk, [&] { return n_ready_ > 0; });
-        Buf &b = bufs_[next_];
-        next_ = (next_ + 1) % 3;
-        if (b.len == 0) {
-            eof_ = true;
-            n_ready_--;
-            return false;
-        }
-        have_cur_ = true;
-        cur_ = b.data.data();
-        pos_ = 0;
-        len_ = b.len;
-        return true;
     }
-    bool gz_ = false, eof_ = false, pending_cr_ = false;
+
+    bool gz_ = false, bgzf_ = false, eof_ = false, pending_cr_ = false, started_ = false, stop_ = false;
+    int decode_threads_ = 2;
     tb::GzStream gzs_;
     int fd_ = -1;
-    Buf bufs_[3];
     std::thread producer_;
+    std::vector<std::thread> workers_;
     std::mutex m_;
     std::condition_variable cv_;
-    int n_ready_ = 0;   // buffers filled and not yet handed back (incl. the parser's current one)
-    int next_ = 0;      // next buffer the parser takes
-    bool have_cur_ = false, stop_ = false;
+    std::deque<ChunkPtr> ordered_, work_;
+    std::vector<ChunkPtr> free_;
+    size_t max_in_flight_ = 3;
+    ChunkPtr cur_chunk_;
     const char *cur_ = nullptr;
     size_t pos_ = 0, len_ = 0;
-    uint64_t bytes_in_ = 0;
+    uint64_t bytes_in_ = 0, bgzf_bytes_ = 0;
     std::string error_;
 };
 
@@ -642,6 +837,9 @@ int tb_classify_fastx(const char *reads_path, const hash_set *A, const hash_set 
 
     Reader reader;
     reader.batch_bases = batch_bases;
+    // a quarter of the host threads may decode BGZF blocks; the parser takes ~2 GB/s, which four
+    // to six decoders fill
+    reader.src.set_threads(std::max(1, std::min(6, threads / 4)));
     if (!reader.src.open(reads_path, reader.error)) {
         fprintf(stderr, "tb_classify_fastx: %s\n", reader.error.c_str());
         return -2;

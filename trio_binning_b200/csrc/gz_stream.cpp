@@ -322,7 +322,7 @@ GzStream::GzStream() { payloads(); }
 
 GzStream::~GzStream()
 {
-    if (fd_ >= 0) ::close(fd_);
+    if (fd_ >= 0 && own_fd_) ::close(fd_);
     delete tables_;
 }
 
@@ -340,9 +340,53 @@ bool GzStream::open(const char *path, std::string &err)
         err = std::string("cannot open ") + path;
         return false;
     }
-    in_.assign(IN_CAP + 16, 0);
-    out_.assign(HIST + OUT_CHUNK + OUT_SLACK, 0);
-    tables_ = new Tables();
+    reset_state();
+    return true;
+}
+
+// buffers are allocated once per object; a GzStream can be re-opened on another source
+void GzStream::reset_state()
+{
+    if (in_.empty()) in_.assign(IN_CAP + 16, 0);
+    if (out_.empty()) out_.assign(HIST + OUT_CHUNK + OUT_SLACK, 0);
+    if (!tables_) tables_ = new Tables();
+    eof_ = false;
+    in_pos_ = in_len_ = 0;
+    in_total_ = 0;
+    out_pos_ = out_taken_ = out_base_ = 0;
+    member_out_ = 0;
+    crc_ = 0;
+    crc_from_ = 0;
+    bitbuf_ = 0;
+    bitcnt_ = 0;
+    final_block_ = false;
+    stored_left_ = 0;
+    mode_ = START;
+    first_member_ = true;
+    mem_ = nullptr;
+    mem_left_ = 0;
+    err_.clear();
+}
+
+bool GzStream::open_fd(int fd, bool at_start)
+{
+    reset_state();
+    fd_ = fd;
+    own_fd_ = false;
+    if (!at_start) {
+        first_member_ = false;
+        mode_ = MEMBER_HEADER;
+    }
+    return true;
+}
+
+bool GzStream::open_memory(const unsigned char *data, size_t len)
+{
+    reset_state();
+    mem_ = data;
+    mem_left_ = len;
+    first_member_ = false;
+    mode_ = MEMBER_HEADER;
     return true;
 }
 
@@ -355,7 +399,17 @@ bool GzStream::fill_input()
         in_pos_ = 0;
     }
     bool got_any = false;
-    while (in_len_ < IN_CAP) {
+    if (mem_) {
+        const size_t n = mem_left_ < IN_CAP - in_len_ ? mem_left_ : IN_CAP - in_len_;
+        memcpy(in_.data() + in_len_, mem_, n);
+        mem_ += n;
+        mem_left_ -= n;
+        in_len_ += n;
+        in_total_ += n;
+        got_any = n > 0;
+        if (mem_left_ == 0) eof_ = true;
+    }
+    while (!mem_ && in_len_ < IN_CAP) {
         const ssize_t n = ::read(fd_, in_.data() + in_len_, IN_CAP - in_len_);
         if (n < 0) {
             if (errno == EINTR) continue;

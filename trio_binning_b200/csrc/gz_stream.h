@@ -26,6 +26,13 @@ public:
     GzStream();
     ~GzStream();
     bool open(const char *path, std::string &err);
+    // Read from an already open descriptor at its current offset (not closed by GzStream).
+    // at_start = true: like open() -- the bytes must be a gzip member, or are passed through;
+    // false: they are treated like what follows a first member -- anything that is not a gzip
+    // member ends the stream silently.
+    bool open_fd(int fd, bool at_start);
+    // Decode from memory (the bytes must stay valid); same "not first member" treatment.
+    bool open_memory(const unsigned char *data, size_t len);
     // Up to `cap` decoded bytes into dst; 0 at end of stream, -1 on error (see error()).
     long read(char *dst, size_t cap);
     const std::string &error() const { return err_; }
@@ -35,6 +42,7 @@ private:
     struct Tables;
     enum Mode { START, PASSTHROUGH, MEMBER_HEADER, BLOCK_HEADER, STORED, HUFFMAN, TRAILER, DONE, FAILED };
 
+    void reset_state();
     bool fill_input();          // slide + read more; false when nothing new could be read
     int parse_member_header();  // 1 parsed, 0 need more input, -1 error / not a member
     int parse_block_header();   // 1 parsed, 0 need more input, -1 error
@@ -43,6 +51,9 @@ private:
     void slide_window();
 
     int fd_ = -1;
+    bool own_fd_ = true;
+    const unsigned char *mem_ = nullptr;  // memory source (open_memory)
+    size_t mem_left_ = 0;
     bool eof_ = false;
     std::vector<unsigned char> in_;
     size_t in_pos_ = 0, in_len_ = 0;
