@@ -210,6 +210,12 @@ int64_t tb_gunzip_fd(const char *path, int out_fd, int64_t chunk);
  * carry-less-multiply path is active on this CPU (testing aids). */
 uint32_t tb_crc32(uint32_t crc, const void *buf, int64_t n);
 int tb_crc32_accelerated(void);
+/* One gzip member for `n` bytes of FASTA/FASTQ text by the writer's FASTQ-aware encoder
+ * (csrc/fastq_deflate.h) into out_buf.  Returns the member's size, -1 if the encoder declines
+ * the text (short lines, tiny input: the writer uses zlib then) or its self-check failed, -2 if
+ * out_cap is too small.  verify != 0: decode and compare before accepting, as the pipeline does
+ * (testing aid; no GPU involved). */
+int64_t tb_fastq_gzip(const void *data, int64_t n, void *out_buf, int64_t out_cap, int verify);
 
 /* Timing marks: record CUDA event `which` (0 or 1) on the slot's stream at the
  * current point of its queue; elapsed() waits for the `to` mark and returns the

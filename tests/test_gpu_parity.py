@@ -494,8 +494,9 @@ def _write_fastq(path, bases, offsets, rng, width=0):
 
 
 def test_native_pipeline_equals_python_io(kmers, capsys, tmp_path):
-    """Same input through the native pipeline (default) and the Python reader/writer
-    (--python-io): identical TSV and identical decompressed outputs, several batches."""
+    """Same input through the native pipeline (default), the Python reader/writer (--python-io)
+    and the native pipeline with its FASTQ-aware gzip encoder (--fastq-gzip): identical TSV and
+    identical decompressed outputs, several batches."""
     import random
 
     from trio_binning_b200 import synth
@@ -510,7 +511,7 @@ def test_native_pipeline_equals_python_io(kmers, capsys, tmp_path):
     reads = tmp_path / "reads.fastq.gz"
     _write_fastq(reads, bases, offsets, random.Random(3))
     outs = {}
-    for mode, extra in (("native", []), ("python", ["--python-io"])):
+    for mode, extra in (("native", []), ("python", ["--python-io"]), ("native_fastq_gzip", ["--fastq-gzip"])):
         d = tmp_path / mode
         d.mkdir()
         argv = ["classify-by-kmers", str(reads), str(pa), str(pb), "--haplotype-a-out-prefix", str(d / "A"),
@@ -524,6 +525,9 @@ def test_native_pipeline_equals_python_io(kmers, capsys, tmp_path):
     assert sorted(outs["native"][1]) == ["A.fastq.gz", "B.fastq.gz", "U.fastq.gz"]
     assert outs["native"][0] == outs["python"][0]
     assert outs["native"][1] == outs["python"][1]
+    # the FASTQ-aware gzip encoder changes the compressed bytes only
+    assert outs["native_fastq_gzip"] == outs["python"]
+    assert "TB_FASTQ_GZIP" not in os.environ
     assert outs["native"][0].count("\n") == 600
     bins = [line.split("\t")[1] for line in outs["native"][0].splitlines()]
     assert {"A", "B", "U"} <= set(bins)

@@ -185,6 +185,8 @@ lib.tb_gunzip_fd.restype = C.c_int64
 lib.tb_crc32.argtypes = [C.c_uint32, C.c_char_p, C.c_int64]
 lib.tb_crc32.restype = C.c_uint32
 lib.tb_crc32_accelerated.restype = C.c_int
+lib.tb_fastq_gzip.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int]
+lib.tb_fastq_gzip.restype = C.c_int64
 
 
 def _error() -> str:
@@ -639,6 +641,19 @@ def gunzip(path: str, chunk: int = 0) -> bytes:
         data = tmp.read()
     assert len(data) == n
     return data
+
+
+def fastq_gzip(text: bytes, verify: bool = True) -> Optional[bytes]:
+    """One gzip member for FASTA/FASTQ text by the writer's FASTQ-aware encoder, or None where
+    it declines (short lines, tiny input) and the writer would use zlib (testing aid)."""
+    cap = len(text) * 2 + 65536
+    buf = C.create_string_buffer(cap)
+    n = lib.tb_fastq_gzip(text, len(text), buf, cap, 1 if verify else 0)
+    if n == -1:
+        return None
+    if n < 0:
+        raise RuntimeError(f"tb_fastq_gzip failed ({n})")
+    return buf.raw[:n]
 
 
 def crc32(data: bytes, crc: int = 0) -> int:
