@@ -185,3 +185,30 @@ def test_bgzf_damage_is_an_error(tmp_path):
         p.write_bytes(bytes(fn(blob)))
         with pytest.raises(RuntimeError, match="gzip"):
             kmers.fastx_dump(str(p))
+
+
+def test_line_endings_across_the_4_mib_chunks_of_the_read_ahead(kmers, seq, tmp_path):
+    """The reader hands the parser 4 MiB chunks: a "\\r\\n" split exactly at a chunk edge must still
+    be one line end, a lone "\\r" there a line end of its own, and records must survive the cut --
+    plain and gzip (the inflate has chunk edges of its own, at other offsets)."""
+    edge = 4 << 20
+    for flavour in ("crlf_split", "cr_last", "lf_first"):
+        head = b">first record\r\n"
+        filler_len = edge - len(head) - (1 if flavour != "lf_first" else 0)
+        if flavour == "crlf_split":      # ...'\r' is the last byte of chunk 1, '\n' the first of chunk 2
+            body = b"A" * filler_len + b"\r\n" + b"CCCC\r\n>second\r\nGGGG\r\n"
+        elif flavour == "cr_last":       # a lone '\r' ends chunk 1, chunk 2 starts with sequence
+            body = b"A" * filler_len + b"\r" + b"CCCC\r>second\rGGGG\r"
+        else:                            # '\n' is the first byte of chunk 2
+            body = b"A" * filler_len + b"\n" + b"CCCC\n@third\nGG\n+\n!!\n"
+        raw = head + body
+        assert raw[edge - 1:edge + 1] in (b"\r\n", b"\rC", b"A\n")
+        plain = tmp_path / f"{flavour}.fa"
+        plain.write_bytes(raw)
+        want = _python_records(seq, plain)
+        assert len(want) >= 2
+        assert kmers.fastx_dump(str(plain)) == want, flavour
+        gz = tmp_path / f"{flavour}.fa.gz"
+        with gzip.open(gz, "wb", compresslevel=1) as f:
+            f.write(raw)
+        assert kmers.fastx_dump(str(gz)) == want, flavour + " (gz)"
