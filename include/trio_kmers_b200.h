@@ -216,6 +216,12 @@ int tb_crc32_accelerated(void);
  * out_cap is too small.  verify != 0: decode and compare before accepting, as the pipeline does
  * (testing aid; no GPU involved). */
 int64_t tb_fastq_gzip(const void *data, int64_t n, void *out_buf, int64_t out_cap, int verify);
+/* Copy in_fd to the gzip file out_path through the pipeline's output writer: text cut into chunks
+ * that n_threads workers compress as independent gzip members, written in order, `piece` bytes
+ * appended at a time; fastq_encoder != 0 tries the FASTQ-aware encoder before zlib.  Returns the
+ * number of input bytes or < 0 (testing aid; no GPU involved; the reference writes through
+ * Python's gzip.open, seq.py:132-134). */
+int64_t tb_gzip_copy(int in_fd, const char *out_path, int level, int n_threads, int fastq_encoder, int64_t piece);
 
 /* Timing marks: record CUDA event `which` (0 or 1) on the slot's stream at the
  * current point of its queue; elapsed() waits for the `to` mark and returns the

@@ -98,3 +98,26 @@ def test_random_line_structures(pieces):
     member = kmers.fastq_gzip(text)
     if member is not None:
         assert gzip.decompress(member) == text
+
+
+@pytest.mark.parametrize("fastq_encoder", [False, True])
+def test_parallel_member_writer_keeps_order(kmers, tmp_path, fastq_encoder):
+    """The output writer cuts the text into 4 MB chunks, compresses them on a thread pool as
+    independent gzip members and writes them in order (with back-pressure): the file must
+    decompress to exactly the input, whatever the piece size the text arrives in."""
+    text = _fastq(700, 20_000, 7, "runs")  # ~28 MB: several chunks per run
+    src = tmp_path / "in.fastq"
+    src.write_bytes(text)
+    for piece, threads, level in ((1 << 16, 3, 1), (4_000_001, 2, 6 if fastq_encoder else 1), (123_457, 1, 1)):
+        out = tmp_path / f"out_{piece}.gz"
+        assert kmers.gzip_copy(str(src), str(out), level=level, threads=threads, fastq_encoder=fastq_encoder,
+                               piece=piece) == len(text)
+        blob = out.read_bytes()
+        assert gzip.decompress(blob) == text
+        assert blob.count(b"\x1f\x8b\x08") >= 3  # several members
+        assert kmers.gunzip(str(out)) == text  # and our own reader agrees
+    empty = tmp_path / "empty"
+    empty.write_bytes(b"")
+    out = tmp_path / "empty.gz"
+    assert kmers.gzip_copy(str(empty), str(out), fastq_encoder=fastq_encoder) == 0
+    assert gzip.decompress(out.read_bytes()) == b""  # Python always writes a valid empty gzip file

@@ -1087,4 +1087,37 @@ int64_t tb_fastx_dump(const char *reads_path, int out_fd)
     return n;
 }
 
+
+// exposed for tests: copy in_fd to the gzip file out_path through the pipeline's writer (chunks
+// compressed in parallel as independent members, written in order), feeding it `piece` bytes at a
+// time.  fastq_encoder != 0 tries the FASTQ-aware encoder first.  Returns the number of input
+// bytes, or < 0.
+int64_t tb_gzip_copy(int in_fd, const char *out_path, int level, int n_threads, int fastq_encoder, int64_t piece)
+{
+    if (!out_path || piece < 1) return -1;
+    if (level < 0 || level > 9) level = 6;
+    Pool pool(std::max(1, n_threads));
+    GzFileWriter w;
+    w.pool = &pool;
+    w.level = level;
+    w.fastq_encoder = fastq_encoder != 0;
+    w.max_inflight = 3;  // exercise the back-pressure path
+    if (!w.open(out_path)) return -2;
+    std::vector<char> buf((size_t)piece);
+    int64_t total = 0;
+    for (;;) {
+        const ssize_t n = ::read(in_fd, buf.data(), buf.size());
+        if (n < 0) {
+            if (errno == EINTR) continue;
+            return -3;
+        }
+        if (n == 0) break;
+        w.append(buf.data(), (size_t)n);
+        w.drain(false);
+        total += n;
+    }
+    w.finish();
+    return w.failed ? -4 : total;
+}
+
 }  // extern "C"

@@ -187,6 +187,8 @@ lib.tb_crc32.restype = C.c_uint32
 lib.tb_crc32_accelerated.restype = C.c_int
 lib.tb_fastq_gzip.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int]
 lib.tb_fastq_gzip.restype = C.c_int64
+lib.tb_gzip_copy.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int64]
+lib.tb_gzip_copy.restype = C.c_int64
 
 
 def _error() -> str:
@@ -654,6 +656,16 @@ def fastq_gzip(text: bytes, verify: bool = True) -> Optional[bytes]:
     if n < 0:
         raise RuntimeError(f"tb_fastq_gzip failed ({n})")
     return buf.raw[:n]
+
+
+def gzip_copy(in_path: str, out_path: str, level: int = 6, threads: int = 2, fastq_encoder: bool = False,
+              piece: int = 1 << 16) -> int:
+    """Compress a file with the native pipeline's output writer (testing aid, no GPU needed)."""
+    with open(in_path, "rb") as f:
+        n = lib.tb_gzip_copy(f.fileno(), os.fsencode(out_path), level, threads, 1 if fastq_encoder else 0, piece)
+    if n < 0:
+        raise RuntimeError(f"tb_gzip_copy failed ({n})")
+    return int(n)
 
 
 def crc32(data: bytes, crc: int = 0) -> int:
