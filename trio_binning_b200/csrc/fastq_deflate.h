@@ -14,6 +14,10 @@
 // The output is a standard gzip member (RFC 1951/1952).  Every member is decoded again with the
 // reader's own inflate (gz_stream.cpp) and compared with the input before it is accepted; the
 // caller falls back to zlib if that ever fails or if the text is not worth it (short lines).
+// (Short reads were tried -- mixed blocks, read names matched against the previous name -- and
+// dropped: on 150-bp reads with binned qualities a Huffman code cannot go below one bit per
+// quality character, and the result was 34 % of the input against 31 % for zlib -1 at a similar
+// speed.)
 #pragma once
 #include <stddef.h>
 
