@@ -62,10 +62,10 @@ int main(int argc, char **argv)
     const int rc = tb_classify_fastx(argv[1], &A, &B, a.c_str(), b.c_str(), u.c_str(), argc > 5 ? atoi(argv[5]) : 1,
                                      fileno(t), argc > 3 ? atoll(argv[3]) : 1000000, argc > 4 ? atoi(argv[4]) : 4, &st);
     fclose(t);
-    printf("rc=%d reads=%llu bases=%llu batches=%llu A/B/U=%llu/%llu/%llu raw=%llu gz=%llu  %.2f s (parse %.2f, write %.2f)\n", rc,
+    printf("rc=%d reads=%llu bases=%llu batches=%llu A/B/U=%llu/%llu/%llu raw=%llu gz=%llu  %.2f s (parse %.2f, classify wait %.2f, write %.2f)\n", rc,
            (unsigned long long)st.n_reads, (unsigned long long)st.n_bases, (unsigned long long)st.n_batches,
            (unsigned long long)st.reads_a, (unsigned long long)st.reads_b, (unsigned long long)st.reads_u,
            (unsigned long long)st.output_raw_bytes, (unsigned long long)st.output_gz_bytes, st.seconds_total,
-           st.seconds_parse, st.seconds_write);
+           st.seconds_parse, st.seconds_gpu_wait, st.seconds_write);
     return rc ? 1 : 0;
 }

@@ -782,6 +782,7 @@ struct GzFileWriter {
     size_t max_inflight = 64;  // back-pressure: at most this many chunks being compressed
     void append(const char *p, size_t n)
     {
+        if (pending.capacity() < kChunk) pending.reserve(kChunk + (kChunk >> 2));  // no regrowth copies
         pending.append(p, n);
         if (pending.size() >= kChunk) {
             dispatch(std::move(pending));
