@@ -105,7 +105,8 @@ void tb_host_free(void *p);
 /* Sets. */
 hash_set *tb_set_create_from_file(const char *path, int device);
 /* keys: RAW LSB-first 2-bit encodings (c/kmers.c:50-72) in host memory;
- * num_kmers := n (as if the file had n lines). */
+ * num_kmers := n (as if the file had n lines).  A key that is not below 4^k is not the
+ * kmer_to_int value of any k-mer: the call fails (NULL) instead of storing it. */
 hash_set *tb_set_create_from_keys(const uint64_t *keys, uint64_t n, int k, int device);
 void tb_set_destroy(hash_set *s);
 /* membership of already-encoded lookup keys (host arrays), for tests */
@@ -197,14 +198,16 @@ int tb_classify_fastx(const char *reads_path, const hash_set *A, const hash_set 
                       int tsv_fd, int64_t batch_bases, int n_threads, tb_stream_stats *stats);
 /* Python's repr(float) of x into buf (testing aid for the TSV writer). */
 int tb_float_repr(double x, char *buf, int buf_len);
-/* Parse a file with the native reader and write "name<TAB>seq<TAB>qual|<None>" per record
- * to out_fd (testing aid; no GPU involved).  Returns the number of records, or < 0: -1 cannot
+/* Parse a file with the native reader and write every record to out_fd as three
+ * length-prefixed fields -- name, sequence, quality; each an int64 (little-endian) length
+ * followed by the bytes, length -1 for "no quality" (testing aid; no GPU involved).  Returns the number of records, or < 0: -1 cannot
  * open, -2 unreadable input (corrupt gzip data; message in tb_last_error), -3 out of memory. */
 int64_t tb_fastx_dump(const char *reads_path, int out_fd);
-/* Decode a gzip file (or pass a non-gzip file through) with the pipeline's own streaming
- * inflate, `chunk` bytes per read call, and write the result to out_fd (testing aid; no GPU
- * involved).  Returns the number of bytes written, -1 cannot open, -2 corrupt input, -3 write
- * error.  Replaces what the reference gets from Python's gzip module (seq.py:88-92). */
+/* Decode a gzip file with the pipeline's own streaming inflate, `chunk` bytes per read call,
+ * and write the result to out_fd (testing aid; no GPU involved).  File semantics are those of
+ * Python's gzip module: members concatenated, zero padding after a member skipped, anything
+ * else that is not gzip is an error.  Returns the number of bytes written, -1 cannot open,
+ * -2 corrupt / non-gzip input, -3 write error.  Replaces what the reference gets from Python's gzip module (seq.py:88-92). */
 int64_t tb_gunzip_fd(const char *path, int out_fd, int64_t chunk);
 /* The gzip CRC-32 the reader verifies members with (zlib crc32() semantics), and whether its
  * carry-less-multiply path is active on this CPU (testing aids). */

@@ -89,6 +89,14 @@ typedef struct {
     int hash_size;
     unsigned char k;
     int num_kmers;
+    /* ---- oracle-only extension (after the reference's 32 bytes) ----
+     * sorted != NULL: the set's keys live in a caller-owned ascending array and membership is
+     * a binary search instead of the reference's probe sequence.  Membership does not depend
+     * on the table layout, so every count is unchanged; this form exists because
+     * building the reference's table for 400 M keys takes minutes of random DRAM stores.
+     * Pinned against the hash-table form in tests/test_oracle.py. */
+    const uint64_t *sorted;
+    uint64_t n_sorted;
 } orc_hash_set;
 
 /* c/kmers.c:160-180 -- hash_size = num_kmers*4/3 computed in 64 bits, stored in int. */
@@ -133,6 +141,14 @@ int orc_set_add_int(orc_hash_set *s, uint64_t key)
 /* c/kmers.c:257-265 -- probe until an empty slot; Q6: stop after hash_size. */
 int orc_set_contains_int(const orc_hash_set *s, uint64_t key)
 {
+    if (s->sorted) {
+        uint64_t lo = 0, hi = s->n_sorted; /* first index with sorted[i] >= key */
+        while (lo < hi) {
+            uint64_t mid = lo + (hi - lo) / 2;
+            if (s->sorted[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        return lo < s->n_sorted && s->sorted[lo] == key;
+    }
     if (s->hash_size <= 0) return 0;
     unsigned int pos = orc_hash_function(key) % (unsigned int)s->hash_size;
     for (int n = 0; n < s->hash_size && s->full[pos]; n++) {
@@ -217,6 +233,19 @@ orc_hash_set *orc_set_from_ints(const uint64_t *keys, uint64_t n, int k)
     orc_hash_set *s = orc_set_new(k, n);
     for (uint64_t i = 0; i < n; i++)
         orc_set_add_int(s, keys[i]);
+    return s;
+}
+
+/* Same set, keys given as an ASCENDING array that the caller keeps alive (duplicates allowed:
+ * num_kmers := n, as if the file had n lines).  No table is built. */
+orc_hash_set *orc_set_from_sorted(const uint64_t *keys, uint64_t n, int k)
+{
+    orc_hash_set *s = (orc_hash_set *)calloc(1, sizeof *s);
+    s->k = (unsigned char)k;
+    s->num_kmers = (int)n;
+    s->hash_size = (int)(n * 4 / 3);
+    s->sorted = keys;
+    s->n_sorted = n;
     return s;
 }
 

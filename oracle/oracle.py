@@ -56,6 +56,8 @@ class Oracle:
         lib.orc_set_from_file.restype = P
         lib.orc_set_from_ints.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
         lib.orc_set_from_ints.restype = P
+        lib.orc_set_from_sorted.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
+        lib.orc_set_from_sorted.restype = P
         lib.orc_set_free.argtypes = [P]
         lib.orc_set_contains_int.argtypes = [P, C.c_uint64]
         lib.orc_set_contains_int.restype = C.c_int
@@ -94,7 +96,18 @@ class Oracle:
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         return self.lib.orc_set_from_ints(keys.ctypes.data, len(keys), k)
 
+    def set_from_sorted(self, keys, k):
+        """Set over an ASCENDING uint64 array (membership by binary search, no table build):
+        for the full-size configs, where the reference's table would take minutes to fill.
+        The array is kept alive by this Oracle object."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        s = self.lib.orc_set_from_sorted(keys.ctypes.data, len(keys), k)
+        self._keep = getattr(self, "_keep", {})
+        self._keep[C.addressof(s.contents)] = keys
+        return s
+
     def set_free(self, s):
+        getattr(self, "_keep", {}).pop(C.addressof(s.contents), None)
         self.lib.orc_set_free(s)
 
     def contains(self, s, key):
@@ -116,6 +129,29 @@ class Oracle:
         cb = np.zeros(n, dtype=np.int32)
         self.lib.orc_count_kmers_in_reads(bases.ctypes.data, offsets.ctypes.data, n, A, B,
                                           ca.ctypes.data, cb.ctypes.data)
+        return ca, cb
+
+    def count_batch_threads(self, bases, offsets, A, B, threads=None):
+        """count_batch over `threads` host threads (ctypes drops the GIL; sets are read-only)."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        threads = max(1, min(threads or (os.cpu_count() or 1), n))
+        ca = np.zeros(n, dtype=np.int32)
+        cb = np.zeros(n, dtype=np.int32)
+        # slices of about equal numbers of bases
+        cuts = np.searchsorted(offsets, np.linspace(0, offsets[-1], threads * 4 + 1)[1:-1])
+        bounds = np.unique(np.concatenate([[0], cuts, [n]]))
+
+        def work(i):
+            lo, hi = int(bounds[i]), int(bounds[i + 1])
+            self.lib.orc_count_kmers_in_reads(bases.ctypes.data, offsets[lo:].ctypes.data, hi - lo, A, B,
+                                              ca[lo:].ctypes.data, cb[lo:].ctypes.data)
+
+        with ThreadPoolExecutor(threads) as pool:
+            list(pool.map(work, range(len(bounds) - 1)))
         return ca, cb
 
     def scaling_factors(self, na, nb):

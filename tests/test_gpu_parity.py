@@ -628,3 +628,129 @@ def test_short_read_volume_vs_oracle_subsample(kmers, oracle, k):
     oracle.set_free(ob)
     kmers.destroy_kmer_hash_set(A)
     kmers.destroy_kmer_hash_set(B)
+
+
+# ---------------------------------------------------------------- round-2 additions
+def test_kmer_in_hash_set_reference_signature(kmers, oracle, fixture_sets):
+    """kmer_in_hash_set through the reference's own signature (c/kmers.c:245-268):
+    char kmer_in_hash_set(char *kmer, char *empty_kmer_buffer, hash_set *set) -- canonical
+    min(fwd, revcomp) lookup, the scratch buffer receives the reverse complement and keeps its
+    old bytes where the k-mer holds a non-ACGT byte (quirk Q3)."""
+    import ctypes as C
+
+    a, b = fixture_sets
+    lines_a = open(os.path.join(REF_DATA, "hapA.txt")).read().split()
+    lines_b = open(os.path.join(REF_DATA, "hapB.txt")).read().split()
+    oa = oracle.set_from_file(os.path.join(REF_DATA, "hapA.txt"))
+
+    def call(kmer, s, scratch=b"x" * 21):
+        buf = C.create_string_buffer(scratch, 22)
+        got = kmers.lib.kmer_in_hash_set(kmer.encode(), buf, s)
+        return got != b"\x00", buf.raw[:21].decode("latin-1")
+
+    for line in lines_a:
+        rc = kmers.reverse_complement(line)
+        # every fixture k-mer is findable (SURVEY Q1), in either orientation
+        assert call(line, a) == (True, rc)
+        assert call(rc, a) == (True, line)
+        assert call(line, b)[0] is False
+        key = min(oracle.kmer_to_int(line), oracle.kmer_to_int(rc))
+        assert oracle.contains(oa, key)
+    for line in lines_b:
+        assert call(line, b)[0] is True and call(line, a)[0] is False
+    # Q1: a stored k-mer larger than its reverse complement is unfindable in either orientation
+    unfindable = "TTTTCAAAGCTTCTTAGAGGT"  # its reverse complement is hapA's line 1 (SURVEY appendix B.5)
+    s = kmers.create_kmer_hash_set_from_ints(np.array([kmers.kmer_to_int(unfindable)], dtype=np.uint64), 21)
+    assert call(unfindable, s)[0] is False and call(kmers.reverse_complement(unfindable), s)[0] is False
+    kmers.destroy_kmer_hash_set(s)
+    # Q3: a non-ACGT byte leaves the scratch slot as it was; forward code 0
+    found, buf = call("ACGTNACGTACGTACGTACGT", a, scratch=b"." * 21)
+    assert buf == kmers.reverse_complement("ACGTAACGTACGTACGTACGT")[:16] + "." + kmers.reverse_complement("ACGTAACGTACGTACGTACGT")[17:]
+    assert found is False
+    # agreement with the oracle on random k-mers, both strands, members and non-members
+    from trio_binning_b200 import synth
+
+    ka, _ = synth.random_kmer_sets(500, 1, 21, seed=3)
+    S = kmers.create_kmer_hash_set_from_ints(ka, 21)
+    oS = oracle.set_from_ints(ka, 21)
+    probe = np.concatenate([ka[:200], synth.revcomp_ints(ka[200:400], 21), synth.random_kmer_sets(100, 1, 21, seed=4)[0]])
+    n_found = 0
+    for key in probe.tolist():
+        text = synth.ints_to_ascii(np.array([key], dtype=np.uint64), 21).tobytes().decode()
+        rc = oracle.reverse_complement(text)
+        want = oracle.contains(oS, min(oracle.kmer_to_int(text), oracle.kmer_to_int(rc)))
+        assert call(text, S) == (want, rc)
+        n_found += want
+    assert 50 < n_found < 400
+    oracle.set_free(oS)
+    kmers.destroy_kmer_hash_set(S)
+
+
+def test_keys_outside_the_kmer_space_are_rejected(kmers):
+    """a raw key with bits above 2k set would land in the pair table's tag bits."""
+    good = np.array([1, 2, 3, (1 << 42) - 1], dtype=np.uint64)
+    s = kmers.create_kmer_hash_set_from_ints(good, 21)
+    assert s.contents.n_distinct == 4
+    kmers.destroy_kmer_hash_set(s)
+    for bad in (1 << 42, 1 << 62, (1 << 64) - 1):
+        with pytest.raises(RuntimeError, match="4\\^k"):
+            kmers.create_kmer_hash_set_from_ints(np.array([1, bad, 2], dtype=np.uint64), 21)
+    s = kmers.create_kmer_hash_set_from_ints(np.array([(1 << 64) - 1, 5], dtype=np.uint64), 32)  # k=32: all 64 bits are digits
+    assert s.contents.n_distinct == 1 and s.contents.has_all_ones == 1
+    kmers.destroy_kmer_hash_set(s)
+
+
+@pytest.mark.parametrize("k", list(range(11, 33)))
+def test_every_k_vs_oracle(kmers, oracle, k):
+    """Every k from 11 to 32: 13..31 run the unrolled phase 1 instantiated for that k, 11/12
+    the runtime-k body, 32 the two-table kernel.  Clean and dirty (non-ACGT) spans, long and
+    150-bp reads, text-file loader (so `k` really comes from the file's first line)."""
+    import tempfile
+
+    from trio_binning_b200 import synth
+
+    ka, kb = synth.random_kmer_sets(30_000, 20_000, k, seed=100 + k)
+    with tempfile.TemporaryDirectory() as tmp:
+        pa, pb = os.path.join(tmp, "a.txt"), os.path.join(tmp, "b.txt")
+        synth.write_kmer_file(pa, ka, k)
+        synth.write_kmer_file(pb, kb, k)
+        A, B = kmers.create_kmer_hash_set(pa), kmers.create_kmer_hash_set(pb)
+    assert A.contents.k == k and kmers.get_number_kmers_in_set(A) == len(ka)
+    oa, ob = _oracle_sets(oracle, ka, kb, k)
+    for n_reads, mean_len, fixed, invalid in ((150, 4000, False, 0.0), (150, 3000, False, 0.01), (3000, 150, True, 0.001)):
+        bases, offsets, _ = synth.random_reads(n_reads, mean_len, k, ka, kb, seed=k + n_reads, plant_every=100,
+                                               fixed_len=fixed, invalid_rate=invalid)
+        ca, cb, *_ = kmers.classify_packed(bases, offsets, A, B)
+        wa, wb = oracle.count_batch(bases, offsets, oa, ob)
+        assert (ca == wa).all() and (cb == wb).all(), (k, n_reads, np.nonzero((ca != wa) | (cb != wb))[0][:10])
+        assert wa.sum() > 0 and wb.sum() > 0
+    oracle.set_free(oa)
+    oracle.set_free(ob)
+    kmers.destroy_kmer_hash_set(A)
+    kmers.destroy_kmer_hash_set(B)
+
+
+def test_canonical_orientation_sets(kmers, oracle):
+    """SURVEY 8(d) asks for both set generators: raw orientation (about half of the stored k-mers
+    unfindable, Q1 -- every other synthetic test) and LSB-first-canonical orientation, where every
+    stored k-mer is findable: twice the hits per planted k-mer, same kernels."""
+    from trio_binning_b200 import synth
+
+    k = 21
+    ka, kb = synth.random_kmer_sets(200_000, 200_000, k, seed=8, canonical=True)
+    assert (ka <= synth.revcomp_ints(ka, k)).all()
+    bases, offsets, hap = synth.random_reads(2000, 5000, k, ka, kb, seed=9, plant_every=500)
+    A, B = kmers.create_kmer_hash_set_from_ints(ka, k), kmers.create_kmer_hash_set_from_ints(kb, k)
+    oa, ob = _oracle_sets(oracle, ka, kb, k)
+    ca, cb, sa, sb, bins = kmers.classify_packed(bases, offsets, A, B)
+    wa, wb = oracle.count_batch(bases, offsets, oa, ob)
+    assert (ca == wa).all() and (cb == wb).all()
+    # every planted k-mer is found (none overwritten by a later plant is rare): ~1 hit per 500 bases
+    planted = int(((np.diff(offsets)[hap == 0] - k) // 500).clip(1).sum())
+    assert ca[hap == 0].sum() > 0.9 * planted
+    ra, rb = synth.random_kmer_sets(200_000, 200_000, k, seed=8, canonical=False)
+    assert abs((ra <= synth.revcomp_ints(ra, k)).mean() - 0.5) < 0.01  # raw: half findable
+    oracle.set_free(oa)
+    oracle.set_free(ob)
+    kmers.destroy_kmer_hash_set(A)
+    kmers.destroy_kmer_hash_set(B)

@@ -1,7 +1,7 @@
 """The native reader's own streaming inflate (csrc/gz_stream.cpp) against Python's gzip/zlib --
 what the reference reads its input with (seq.py:88-92).  CPU only.  Semantics pinned here are
-those of zlib's gzread, which the reader used before: concatenated members, pass-through of
-non-gzip data, trailing non-member bytes ignored; every CRC-32 / ISIZE verified."""
+those of Python's gzip module: concatenated members, zero padding skipped, anything else that is
+not gzip is an error; every CRC-32 / ISIZE verified."""
 import gzip
 import os
 import struct
@@ -86,16 +86,34 @@ def test_members_concatenated_and_trailing_bytes(kmers, tmp_path):
     parts = [c["fastq"], b"", c["short"], c["zeros"][:70_000], c["random"][:50_000]]
     blob = b"".join(_member(x, lvl) for x, lvl in zip(parts, (6, 9, 1, 6, 0)))
     _check(kmers, tmp_path, blob, b"".join(parts))
-    # bytes after the last member that are not a member: ignored, as gzread does
+    # zero padding after (and between) members is skipped, as Python's gzip module does
     _check(kmers, tmp_path, blob + bytes(100), b"".join(parts), name="pad.gz", chunks=(0,))
-    _check(kmers, tmp_path, blob + b"garbage, not gzip", b"".join(parts), name="junk.gz", chunks=(0,))
+    two = _member(parts[0]) + bytes(13) + _member(parts[2]) + bytes(1)
+    assert gzip.decompress(two) == parts[0] + parts[2]
+    _check(kmers, tmp_path, two, parts[0] + parts[2], name="pad_between.gz", chunks=(0, 7))
+    # anything else after a member is an error upstream (gzip.BadGzipFile) and here
+    for i, junk in enumerate((b"garbage, not gzip", bytes(5) + b"x", b"\x1f", b"\x1f\x8b\x08")):
+        p = tmp_path / f"junk{i}.gz"
+        p.write_bytes(blob + junk)
+        with pytest.raises((gzip.BadGzipFile, EOFError)):
+            gzip.decompress(blob + junk)
+        with pytest.raises(ValueError):
+            kmers.gunzip(str(p))
 
 
-def test_not_gzip_is_passed_through(kmers, tmp_path):
-    data = _corpus()["fastq"]
-    _check(kmers, tmp_path, data, data, name="plain.gz")
+def test_not_gzip_is_an_error_like_pythons_gzip(kmers, tmp_path):
+    """The reference opens *.gz with gzip.open (seq.py:88-92): a file of that name that is not
+    gzip raises there and must not be read as text here; an empty file reads as empty in both."""
     _check(kmers, tmp_path, b"", b"", name="empty_file.gz", chunks=(0,))
-    _check(kmers, tmp_path, b"\x1f", b"\x1f", name="one_byte.gz", chunks=(0,))
+    assert gzip.decompress(b"") == b""
+    for i, data in enumerate((_corpus()["fastq"], b"\x1f", b"A", b"\x00\x00")):
+        p = tmp_path / f"plain{i}.gz"
+        p.write_bytes(data)
+        with pytest.raises((gzip.BadGzipFile, EOFError)):
+            with gzip.open(p, "rb") as f:
+                f.read()
+        with pytest.raises(ValueError):
+            kmers.gunzip(str(p))
 
 
 def test_optional_header_fields(kmers, tmp_path):

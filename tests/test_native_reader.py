@@ -5,6 +5,7 @@ call, `readfq(open(name, "r"))` / `gzip.open(name, "rt")`, so text-mode universa
 apply on both sides), and seq.py itself is pinned to the reference's readfq by
 tests/test_seq.py.  Records must not contain TABs for the dump format used here."""
 import gzip
+import os
 import random
 
 import pytest
@@ -185,6 +186,54 @@ def test_bgzf_damage_is_an_error(tmp_path):
         p.write_bytes(bytes(fn(blob)))
         with pytest.raises(RuntimeError, match="gzip"):
             kmers.fastx_dump(str(p))
+
+
+def test_bgzf_forged_isize_is_an_error_not_an_abort(tmp_path):
+    """blocks claiming ISIZE = 0xFFFFFFFF made a worker thread throw bad_alloc and
+    std::terminate killed the process.  A BGZF block holds at most 64 KiB: larger claims go to the
+    serial decoder, which reports the corruption through tb_last_error."""
+    import struct
+    import subprocess
+    import sys
+
+    from trio_binning_b200 import kmers
+
+    _, text = _fastq_text(100, 3000, 23)
+    blob = bytearray(_bgzf(text, eof_marker=False))
+    # every block's trailer: CRC32, ISIZE -- forge ISIZE in all of them
+    pos = 0
+    while pos < len(blob):
+        total = struct.unpack_from("<H", blob, pos + 16)[0] + 1
+        for claim in (0xFFFFFFFF,):
+            struct.pack_into("<I", blob, pos + total - 4, claim)
+        pos += total
+    p = tmp_path / "forged.fastq.gz"
+    p.write_bytes(bytes(blob))
+    # in a child process: the failure mode being guarded against is abort(), not an exception
+    code = ("import sys; sys.path.insert(0, %r)\nfrom trio_binning_b200 import kmers\n"
+            "try:\n    kmers.fastx_dump(%r)\nexcept RuntimeError as e:\n    print('ERR', e); sys.exit(7)\n"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(p)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 7 and "gzip" in r.stdout, (r.returncode, r.stdout, r.stderr[-500:])
+    # a moderately wrong ISIZE (70 000 > 64 KiB) takes the same road
+    blob2 = bytearray(_bgzf(text, eof_marker=False))
+    total = struct.unpack_from("<H", blob2, 16)[0] + 1
+    struct.pack_into("<I", blob2, total - 4, 70_000)
+    p2 = tmp_path / "forged2.fastq.gz"
+    p2.write_bytes(bytes(blob2))
+    with pytest.raises(RuntimeError, match="gzip"):
+        kmers.fastx_dump(str(p2))
+
+
+def test_records_with_tabs_survive_the_dump(kmers, seq, tmp_path):
+    """Names are cut at the first SPACE only (seq.py:61), so tabs stay in names; the dump helper
+    must not split on them."""
+    raw = b">name\twith\ttabs comment\nAC\tGT\n@q\t1\nAC\tG\n+\n!\t!!\n"
+    p = tmp_path / "tabs.fa"
+    p.write_bytes(raw)
+    want = _python_records(seq, p)
+    assert want[0][0] == b"name\twith\ttabs" and want[1][1] == b"AC\tG"
+    assert kmers.fastx_dump(str(p)) == want
 
 
 def test_line_endings_across_the_4_mib_chunks_of_the_read_ahead(kmers, seq, tmp_path):

@@ -257,3 +257,24 @@ def test_ragged_set_file_q5(oracle, tmp_path):
     rk = np.ctypeslib.as_array(r.contents.kmers, (n,))
     ok = np.ctypeslib.as_array(o.contents.kmers, (n,))
     assert (rk[rf == 1] == ok[rf == 1]).all()
+
+
+# ---- the binary-search form of the oracle's set (full-size configs) equals the table form
+@pytest.mark.parametrize("k", [9, 21, 25, 31])
+def test_sorted_set_form_equals_table_form(oracle, k):
+    from trio_binning_b200 import synth
+
+    ka, kb = synth.sorted_disjoint_sets(3000, 2500, k, seed=k)
+    assert np.all(np.diff(ka.astype(np.int64)) > 0) and np.all(np.diff(kb.astype(np.int64)) > 0)
+    assert np.intersect1d(ka, kb).size == 0 and int(max(ka[-1], kb[-1])) < 4 ** k
+    bases, offsets, _ = synth.random_reads(300, 400, k, ka, kb, seed=11, plant_every=60, invalid_rate=0.01)
+    ta, tb = oracle.set_from_ints(ka, k), oracle.set_from_ints(kb, k)
+    sa, sb = oracle.set_from_sorted(ka, k), oracle.set_from_sorted(kb, k)
+    want = oracle.count_batch(bases, offsets, ta, tb)
+    got = oracle.count_batch(bases, offsets, sa, sb)
+    assert (want[0] == got[0]).all() and (want[1] == got[1]).all()
+    assert want[0].sum() > 0 and want[1].sum() > 0
+    thr = oracle.count_batch_threads(bases, offsets, sa, sb, threads=3)
+    assert (want[0] == thr[0]).all() and (want[1] == thr[1]).all()
+    for key in list(ka[:50]) + list(kb[:50]) + [0, 1, 4 ** k - 1]:
+        assert oracle.contains(sa, int(key)) == oracle.contains(ta, int(key))

@@ -34,23 +34,85 @@ def find_nvcc():
     raise RuntimeError("nvcc not found; the CUDA library cannot be built (no CPU fallback exists)")
 
 
-def needs_build():
-    if not os.path.exists(LIB_PATH):
+def have_nvcc():
+    try:
+        find_nvcc()
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    except RuntimeError:
+        return False
 
 
-def build(force=False, verbose=False, extra_flags=()):
-    if not force and not needs_build():
-        return LIB_PATH
-    extra_env = os.environ.get("TB_NVCC_EXTRA", "").split()  # e.g. -DTB_MINI_MIN_BLOCKS=6 (tuning experiments)
-    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags) + extra_env + [os.path.join(CSRC, f) for f in SOURCES]
-    cmd += ["-o", LIB_PATH]
+def source_digest():
+    """Hash of everything the library is built from.  Kept beside the library so that staleness
+    does not depend on file times (a snapshot copied to another machine scrambles them)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    with open(os.path.abspath(__file__), "rb") as fh:
+        h.update(fh.read())
+    h.update(os.environ.get("TB_NVCC_EXTRA", "").encode())
+    return h.hexdigest()
+
+
+DIGEST_PATH = os.path.join(PKG, "kmers_c.build_digest")
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH) or not os.path.exists(DIGEST_PATH):
+        return True
+    with open(DIGEST_PATH) as f:
+        return f.read().strip() != source_digest()
+
+
+def _compile_one(nvcc, src, obj, flags, verbose):
+    cmd = [nvcc] + flags + ["-c", src, "-o", obj]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
+
+
+def build(force=False, verbose=False, extra_flags=()):
+    """Compile every source to build/<name>.o (only those older than their inputs, in parallel)
+    and link the shared library.  One object per translation unit keeps the edit-compile loop
+    of a single kernel file at seconds."""
+    if not force and not needs_build():
+        return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = find_nvcc()
+    extra_env = os.environ.get("TB_NVCC_EXTRA", "").split()  # e.g. -DTB_MINI_MIN_BLOCKS=6 (tuning experiments)
+    cflags = [f for f in NVCC_FLAGS if f not in ("-shared", "-lz")]
+    for drop in ("-cudart", "static"):
+        cflags.remove(drop)
+    cflags += list(extra_flags) + extra_env
+    obj_dir = os.path.join(PKG, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    stamp = os.path.join(obj_dir, "flags.txt")
+    flag_text = " ".join(cflags)
+    if not os.path.exists(stamp) or open(stamp).read() != flag_text:
+        force = True
+    header_time = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+    header_time = max(header_time, os.path.getmtime(os.path.abspath(__file__)))
+    jobs, objs = [], []
+    for name in SOURCES:
+        src = os.path.join(CSRC, name)
+        obj = os.path.join(obj_dir, os.path.splitext(name)[0] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), header_time):
+            jobs.append((src, obj))
+    with ThreadPoolExecutor(max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+        list(pool.map(lambda j: _compile_one(nvcc, j[0], j[1], cflags, verbose), jobs))
+    with open(stamp, "w") as f:
+        f.write(flag_text)
+    link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-lz", "-lpthread", "-o", LIB_PATH]
+    if verbose:
+        print(" ".join(link), file=sys.stderr)
+    subprocess.run(link, check=True)
+    with open(DIGEST_PATH, "w") as f:
+        f.write(source_digest() + "\n")
     return LIB_PATH
 
 

@@ -608,12 +608,16 @@ hash_set *tb_set_create_from_keys(const uint64_t *keys, uint64_t n, int k, int d
         uint64_t m = std::min(chunk, n - i);
         cudaError_t e = cudaMemcpy(d_keys, keys + i, m * 8, cudaMemcpyHostToDevice);
         if (e == cudaSuccess)
-            e = tb_launch_insert_keys(d_keys, m, reinterpret_cast<tb_bucket *>(s->d_table),
+            e = tb_launch_insert_keys(d_keys, m, k, reinterpret_cast<tb_bucket *>(s->d_table),
                                       s->n_buckets, cnt.d, 0);
         if (e != cudaSuccess) { fail("key upload/insert failed: %s", cudaGetErrorString(e)); ok = false; }
     }
     if (ok && cudaDeviceSynchronize() != cudaSuccess) { fail("insert kernel failed"); ok = false; }
     ok = ok && !cnt.read(c);
+    if (ok && c[2]) {
+        fail("a key is not below 4^k (k=%d): not the kmer_to_int value of any %d-mer", k, k);
+        ok = false;
+    }
     if (d_keys) cudaFree(d_keys);
     cudaEventRecord(ev1, 0);
     cudaEventSynchronize(ev1);

@@ -1074,8 +1074,28 @@ cudaError_t tb_launch_classify_pair_mini(const tb_batch_view &b, int k, tb_pair_
     switch (k) {
     case 21: return launch_pair_mini_k<21>(b, k, P, filter, n_sectors, n_bits, p2_width, stream);
     case 31: return launch_pair_mini_k<31>(b, k, P, filter, n_sectors, n_bits, p2_width, stream);
-    default: return launch_pair_mini_k<0>(b, k, P, filter, n_sectors, n_bits, p2_width, stream);
+    default: break;
     }
+    // every other k from 13 to 31 gets the same unrolled phase 1 (all shifts and the number of
+    // m-mers per window are compile-time constants) in the default configuration: two bitmap
+    // bits per key, two survivors per phase-2 round.  The experiment knobs (TB_FILTER_BITS=1,
+    // TB_P2_WIDTH=4) and k < 13 fall back to the runtime-k body, which computes every window's
+    // minimizer from its key: same results, several times slower.
+    if (n_bits == 2 && p2_width < 4) {
+        const unsigned blocks = (unsigned)((b.n_tiles + (g_tpb / 32) - 1) / (g_tpb / 32));
+        switch (k) {
+#define TB_MINI_CASE(KK) \
+        case KK: k_classify_pair_mini<KK, 8, 2, 2><<<blocks, g_tpb, 0, stream>>>(b, k, P, filter, n_sectors); \
+                 return cudaGetLastError();
+        TB_MINI_CASE(13) TB_MINI_CASE(14) TB_MINI_CASE(15) TB_MINI_CASE(16) TB_MINI_CASE(17)
+        TB_MINI_CASE(18) TB_MINI_CASE(19) TB_MINI_CASE(20) TB_MINI_CASE(22) TB_MINI_CASE(23)
+        TB_MINI_CASE(24) TB_MINI_CASE(25) TB_MINI_CASE(26) TB_MINI_CASE(27) TB_MINI_CASE(28)
+        TB_MINI_CASE(29) TB_MINI_CASE(30)
+#undef TB_MINI_CASE
+        default: break;
+        }
+    }
+    return launch_pair_mini_k<0>(b, k, P, filter, n_sectors, n_bits, p2_width, stream);
 }
 
 cudaError_t tb_launch_pair_filter_build_mini(const uint64_t *d_pair_table, uint64_t n_slots, uint32_t *filter,

@@ -254,8 +254,15 @@ private:
                 }
                 if (have - p < total) break;
                 const unsigned char *t = buf.data() + p + total - 4;
+                const size_t isize = (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
+                if (isize > 65536) {
+                    // a BGZF block never holds more than 64 KiB; a larger (untrusted) ISIZE means
+                    // this is not BGZF or it is damaged: the serial decoder reports which
+                    not_bgzf = true;
+                    break;
+                }
                 task->comp.insert(task->comp.end(), buf.data() + p, buf.data() + p + total);
-                task->expect += (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
+                task->expect += isize;
                 p += total;
                 if (task->comp.size() >= kTaskBytes) {
                     if (!enqueue(task, true)) return;
@@ -297,11 +304,16 @@ private:
                 c = work_.front();
                 work_.pop_front();
             }
-            c->data.resize(c->expect ? c->expect : 1);
-            gz.open_memory(c->comp.data(), c->comp.size());
             size_t n = 0;
             bool bad = false;
-            for (;;) {
+            try {
+                c->data.resize(c->expect ? c->expect : 1);
+            } catch (const std::exception &) {  // an exception must not leave a std::thread
+                bad = true;
+                c->why = "out of memory while decoding BGZF blocks";
+            }
+            gz.open_memory(c->comp.data(), c->comp.size());
+            while (!bad) {
                 // one spare byte of room shows an overlong stream instead of truncating it
                 char extra;
                 const long got = n < c->expect ? gz.read(c->data.data() + n, c->expect - n) : gz.read(&extra, 1);
@@ -1058,16 +1070,17 @@ int64_t tb_fastx_dump(const char *reads_path, int out_fd)
         Batch *b = full_q.pop();
         out.clear();
         for (int64_t i = 0; i < b->n(); i++) {
+            // three length-prefixed fields (int64 little-endian; -1 = None): names keep tabs, and
+            // carriage returns or tabs may sit in sequences, so no separator byte is safe
             const Rec &r = b->recs[(size_t)i];
-            out.append(b->text.data() + r.name_off, r.name_len);
-            out += '\t';
-            out.append(b->bases + b->offsets[(size_t)i], (size_t)(b->offsets[(size_t)i + 1] - b->offsets[(size_t)i]));
-            out += '\t';
-            if (r.has_qual)
-                out.append(b->text.data() + r.qual_off, r.qual_len);
-            else
-                out += "<None>";
-            out += '\n';
+            const int64_t seq_len = b->offsets[(size_t)i + 1] - b->offsets[(size_t)i];
+            const int64_t lens[3] = { (int64_t)r.name_len, seq_len, r.has_qual ? (int64_t)r.qual_len : -1 };
+            const char *ptrs[3] = { b->text.data() + r.name_off, b->bases + b->offsets[(size_t)i],
+                                    b->text.data() + r.qual_off };
+            for (int f = 0; f < 3; f++) {
+                out.append(reinterpret_cast<const char *>(&lens[f]), 8);
+                if (lens[f] > 0) out.append(ptrs[f], (size_t)lens[f]);
+            }
             n++;
         }
         size_t off = 0;

@@ -814,8 +814,12 @@ long GzStream::read(char *dst, size_t cap)
                 }
                 if (in_len_ - in_pos_ >= 2 && in_[in_pos_] == 0x1f && in_[in_pos_ + 1] == 0x8b)
                     mode_ = MEMBER_HEADER;
-                else
+                else if (in_len_ == in_pos_)
+                    mode_ = DONE;  // an empty file reads as empty (Python's gzip does the same)
+                else if (lenient_)
                     mode_ = PASSTHROUGH;  // gzread semantics: not gzip -> as is
+                else
+                    fail("not a gzip file (no gzip magic at the start)");  // gzip.BadGzipFile upstream
                 break;
             case PASSTHROUGH: {
                 if (in_pos_ == in_len_) {
@@ -832,18 +836,29 @@ long GzStream::read(char *dst, size_t cap)
                 break;
             }
             case MEMBER_HEADER: {
+                if (!first_member_ && !lenient_) {
+                    // Python's gzip (what the reference reads with, seq.py:88-92) skips zero
+                    // padding after a member; anything else must be another member
+                    while (in_pos_ < in_len_ && in_[in_pos_] == 0) in_pos_++;
+                    if (in_pos_ == in_len_) {
+                        if (!fill_input() && mode_ != FAILED && eof_) mode_ = DONE;
+                        break;
+                    }
+                }
                 const int r = parse_member_header();
                 if (r == 0) {
                     if (!fill_input() && mode_ != FAILED && eof_ && in_len_ - in_pos_ < 10) {
                         // nothing (or less than a header) left
                         if (first_member_) fail("truncated gzip header");
-                        else mode_ = DONE;
+                        else if (lenient_ || in_len_ == in_pos_) mode_ = DONE;
+                        else fail("bytes after the last gzip member are not gzip data");
                     }
                     break;
                 }
                 if (r < 0) {
                     if (first_member_) fail("malformed gzip header");
-                    else mode_ = DONE;  // trailing bytes that are not a member: ignored (gzread)
+                    else if (lenient_) mode_ = DONE;  // gzread: trailing non-member bytes are ignored
+                    else fail("bytes after a gzip member are not another gzip member");
                     break;
                 }
                 crc_ = 0;

@@ -3,12 +3,16 @@
 // SURVEY 8(f) row 1 asks for "faster inflate": at GPU speed the single-stream inflate of the
 // input is the wall of the whole command.  GzStream replaces zlib's gzread with a DEFLATE decoder
 // written for this pipeline (64-bit bit buffer refilled once per symbol group, 11-bit primary
-// litlen table with sub-tables, up to three literals per refill, 8-byte match copies) and keeps
-// gzread's file semantics, which the reader was tested against:
-//   * concatenated gzip members are decoded one after the other (Python's gzip module does the
-//     same for the reference, seq.py:88-92);
-//   * a file that does not start with the gzip magic is passed through unchanged;
-//   * bytes after the last member that are not another member end the stream silently.
+// litlen table with sub-tables, up to three literals per refill, 8-byte match copies) with the
+// file semantics of Python's gzip module, which is what the reference reads *.gz with
+// (seq.py:88-92):
+//   * concatenated gzip members are decoded one after the other;
+//   * an empty file reads as empty; any other file that does not start with the gzip magic is
+//     an error (gzip.BadGzipFile upstream), not text to pass through;
+//   * zero padding after a member is skipped; any other bytes there must be another member,
+//     else the stream is an error (upstream: BadGzipFile "Not a gzipped file").
+// set_lenient(true) restores zlib gzread's behaviour (pass non-gzip through, ignore trailing
+// bytes) for callers that want it; the pipeline does not.
 // Every member's CRC-32 and ISIZE are verified; any inconsistency is an error, never a guess.
 // The algorithm is RFC 1951/1952 as published; nothing here is derived from the reference
 // (which delegates decompression to Python's gzip module).
@@ -27,15 +31,15 @@ public:
     ~GzStream();
     bool open(const char *path, std::string &err);
     // Read from an already open descriptor at its current offset (not closed by GzStream).
-    // at_start = true: like open() -- the bytes must be a gzip member, or are passed through;
-    // false: they are treated like what follows a first member -- anything that is not a gzip
-    // member ends the stream silently.
+    // at_start = true: like open() -- the bytes must start with a gzip member;
+    // false: they are treated like what follows a first member (zero padding, more members).
     bool open_fd(int fd, bool at_start);
     // Decode from memory (the bytes must stay valid); same "not first member" treatment.
     bool open_memory(const unsigned char *data, size_t len);
     // Up to `cap` decoded bytes into dst; 0 at end of stream, -1 on error (see error()).
     long read(char *dst, size_t cap);
     const std::string &error() const { return err_; }
+    void set_lenient(bool on) { lenient_ = on; }  // call before the first read()
     uint64_t compressed_bytes() const { return in_total_; }
 
 private:
@@ -73,6 +77,7 @@ private:
     uint32_t stored_left_ = 0;
     Mode mode_ = START;
     bool first_member_ = true;
+    bool lenient_ = false;
     Tables *tables_ = nullptr;
     std::string err_;
 };

@@ -13,7 +13,8 @@ cudaError_t tb_launch_insert_text(const char *d_text, uint64_t n_lines, uint64_t
                                   int stride, int k, int check_newline, tb_bucket *table,
                                   uint32_t n_buckets, unsigned long long *d_counters,
                                   cudaStream_t stream);
-cudaError_t tb_launch_insert_keys(const uint64_t *d_keys, uint64_t n, tb_bucket *table,
+// keys that are not below 4^k are not inserted; counters[2] |= 1 reports them
+cudaError_t tb_launch_insert_keys(const uint64_t *d_keys, uint64_t n, int k, tb_bucket *table,
                                   uint32_t n_buckets, unsigned long long *d_counters,
                                   cudaStream_t stream);
 // merge a per-set table (empty = ~0) into the pair table (empty = 0); tag 1 = A, 2 = B

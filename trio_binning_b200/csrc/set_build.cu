@@ -80,19 +80,22 @@ k_insert_text(const char *__restrict__ text, uint64_t n_lines, uint64_t text_byt
 }
 
 __global__ void __launch_bounds__(256)
-k_insert_keys(const uint64_t *__restrict__ keys, uint64_t n, tb_bucket *table, uint32_t n_buckets,
-              unsigned long long *counters)
+k_insert_keys(const uint64_t *__restrict__ keys, uint64_t n, uint64_t key_mask, tb_bucket *table,
+              uint32_t n_buckets, unsigned long long *counters)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool is_new = false, all_ones = false;
+    bool is_new = false, all_ones = false, out_of_range = false;
     if (i < n) {
         uint64_t key = keys[i];
-        if (key == TB_EMPTY)
+        if (key & ~key_mask)
+            out_of_range = true;  // not the encoding of any k-mer: reported, never stored (the
+                                  // pair table keeps its tags in the bits a k-mer leaves free)
+        else if (key == TB_EMPTY)
             all_ones = true;
         else
             is_new = insert_key(table, n_buckets, key);
     }
-    account(is_new, all_ones, false, counters);
+    account(is_new, all_ones, out_of_range, counters);
 }
 
 __global__ void __launch_bounds__(256)
@@ -157,12 +160,13 @@ cudaError_t tb_launch_insert_text(const char *d_text, uint64_t n_lines, uint64_t
     return cudaGetLastError();
 }
 
-cudaError_t tb_launch_insert_keys(const uint64_t *d_keys, uint64_t n, tb_bucket *table,
+cudaError_t tb_launch_insert_keys(const uint64_t *d_keys, uint64_t n, int k, tb_bucket *table,
                                   uint32_t n_buckets, unsigned long long *d_counters,
                                   cudaStream_t stream)
 {
     if (n == 0) return cudaSuccess;
-    k_insert_keys<<<blocks_for(n, 256), 256, 0, stream>>>(d_keys, n, table, n_buckets, d_counters);
+    const uint64_t key_mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    k_insert_keys<<<blocks_for(n, 256), 256, 0, stream>>>(d_keys, n, key_mask, table, n_buckets, d_counters);
     return cudaGetLastError();
 }
 

@@ -43,17 +43,22 @@ def _locate_library() -> str:
 
 
 _lib_path = _locate_library()
-if not _lib_path:
-    # Source checkout without a built library: try to build it in-tree with nvcc.
-    try:
-        from . import _build
+try:
+    # Source checkout: (re)build in-tree when the library is missing or older than csrc/
+    # (_build.build() is a no-op when it is current).  A stale library with a missing
+    # compiler is still loaded -- the GPU box has no reason to rebuild what travelled with it.
+    from . import _build
 
+    if not _lib_path or (_build.needs_build() and _build.have_nvcc()):
         _lib_path = _build.build()
-    except Exception as exc:  # noqa: BLE001
+except Exception as exc:  # noqa: BLE001
+    if not _lib_path:
         raise ImportError(
             "Cannot load kmers_c library (the CUDA build for sm_100a is missing and "
             f"could not be produced: {exc}). There is no CPU fallback."
         ) from exc
+    print(f"trio_binning_b200: rebuilding the stale CUDA library failed ({exc}); loading it as it is",
+          file=sys.stderr)
 
 lib = C.cdll.LoadLibrary(_lib_path)
 
@@ -619,18 +624,24 @@ def fastx_dump(reads_path: str):
             raise RuntimeError(f"tb_fastx_dump failed ({n}): {_error()}")
         tmp.seek(0)
         data = tmp.read()
-    out = []
-    for line in data.split(b"\n")[:-1]:
-        name, seq, qual = line.split(b"\t")[0], line.split(b"\t")[1], line.split(b"\t", 2)[2]
-        out.append((name, seq, None if qual == b"<None>" else qual))
+    out, pos = [], 0
+    while pos < len(data):
+        fields = []
+        for _ in range(3):  # length-prefixed: int64 little-endian, -1 = None
+            length = int.from_bytes(data[pos:pos + 8], "little", signed=True)
+            pos += 8
+            fields.append(None if length < 0 else data[pos:pos + length])
+            pos += max(length, 0)
+        out.append(tuple(fields))
     assert len(out) == n
     return out
 
 
 def gunzip(path: str, chunk: int = 0) -> bytes:
-    """Contents of a .gz file (or of a non-gzip file, passed through) as decoded by the native
-    reader's own streaming inflate, read `chunk` bytes at a time (testing aid, no GPU needed).
-    Raises ValueError for corrupt or truncated input."""
+    """Contents of a .gz file as decoded by the native reader's own streaming inflate, read
+    `chunk` bytes at a time (testing aid, no GPU needed).  Raises ValueError for input that is
+    corrupt, truncated, not gzip at all, or followed by bytes that are neither zero padding nor
+    another member -- the cases in which Python's gzip module raises for the reference."""
     import tempfile
 
     with tempfile.TemporaryFile() as tmp:

@@ -52,6 +52,35 @@ def random_kmer_sets(n_a: int, n_b: int, k: int, seed: int, canonical: bool = Fa
     return keys[:n_a].copy(), keys[n_a:].copy()
 
 
+def sorted_disjoint_sets(n_a: int, n_b: int, k: int, seed: int):
+    """Two disjoint sets of distinct k-mers as ASCENDING uint64 arrays, in seconds even for the
+    400 M + 400 M config: the keys are the running sums of random gaps (so they spread over the
+    whole 4^k space, every low-order digit uniform) dealt alternately to A and B.  Sorted arrays
+    let a checker test membership by binary search without building a table.  Raw orientation:
+    about half of the keys are unfindable (quirk Q1)."""
+    rng = np.random.default_rng(seed)
+    n = n_a + n_b
+    space = 1 << (2 * k)
+    if n > space // 4:
+        raise ValueError("k too small for that many distinct k-mers")
+    mean_gap = space // (n + 1) // 16 * 15  # 6 % head-room: the sum's spread is 1/sqrt(3n) of it
+    keys = rng.integers(1, max(2, 2 * mean_gap - 1), size=n, dtype=np.uint64)
+    np.cumsum(keys, out=keys)
+    while int(keys[-1]) >= space:  # only for a handful of keys
+        keys = np.unique(keys >> np.uint64(1))
+        n = len(keys)
+    # deal: pairs (A, B) while both remain, the rest to the larger set
+    m = min(n_a, n_b, n // 2)
+    a = keys[0:2 * m:2]
+    b = keys[1:2 * m:2]
+    rest = keys[2 * m:]
+    if n_a > n_b:
+        a = np.concatenate([a, rest])
+    elif n_b > n_a:
+        b = np.concatenate([b, rest])
+    return np.ascontiguousarray(a), np.ascontiguousarray(b)
+
+
 def ints_to_ascii(keys: np.ndarray, k: int) -> np.ndarray:
     """(N, k) uint8 matrix of the k-mer letters."""
     keys = keys.astype(np.uint64)
