@@ -192,7 +192,52 @@ typedef struct tb_stream_stats {
     uint64_t reads_a, reads_b, reads_u;
     uint64_t output_raw_bytes, output_gz_bytes;
     double seconds_total, seconds_parse, seconds_gpu_wait, seconds_write;
+    /* round 2: where the host time goes.  seconds_parse is the reader thread's wall time (it
+     * includes waiting for the inflate and for free batches); seconds_inflate is the time spent
+     * inside the gzip decoder, summed over its threads; seconds_pack the 2-bit packing;
+     * seconds_deflate_cpu the output compression, summed over the pool's threads;
+     * seconds_gpu_wait is summed over the device workers. */
+    double seconds_inflate, seconds_pack, seconds_deflate_cpu;
+    uint64_t devices_used;
 } tb_stream_stats;
+/* One process, several GPUs: reads are parsed once, packed to 2 bits on the host and dealt
+ * batch by batch to `n_devices` device workers, each with its own replica of the two sets
+ * (sets_a[d] / sets_b[d] live on the device that worker drives; tb_set_clone makes replicas).
+ * Results are merged in input order, so outputs and TSV are byte-identical for any n_devices.
+ * Replaces the reference's per-read loop, classify_by_kmers.py:99-117.
+ *   gzip_output 1: three gzip files out_a/out_b/out_u (seq.py:132-134);
+ *               0: the reference's plain mode (seq.py:127-130): text files out_a and out_u --
+ *                  the B handle is opened on out_a as upstream does (out_b is never created),
+ *                  with CPython's buffering restated so the overlap comes out byte-identical;
+ *   round_robin 0: a worker takes the next batch whenever it has a free slot; 1: batch i goes to
+ *                  device i mod n_devices. */
+typedef struct tb_stream_options {
+    int n_devices;
+    const hash_set *const *sets_a;
+    const hash_set *const *sets_b;
+    int gzip_output, gzip_level, fastq_encoder, round_robin;
+    int tsv_fd;
+    int64_t batch_bases;
+    int n_threads;
+    /* plain output only: which interpreter's text writer to restate -- when TextIOWrapper.write
+     * flushes its pending list before taking a new string: 0 = the string alone is >= 8192
+     * bytes (CPython 3.9 .. 3.12), 1 = list + string would exceed 8192 bytes (later versions),
+     * 2 = never (3.8) -- and the BufferedWriter's size (0 = the file's st_blksize).  The
+     * Python caller probes both on the running interpreter. */
+    int py_text_mode;
+    int64_t py_buffer_size;
+} tb_stream_options;
+int tb_classify_fastx_multi(const char *reads_path, const tb_stream_options *opt, const char *out_a,
+                            const char *out_b, const char *out_u, tb_stream_stats *stats);
+/* Replica of a set on another device (table copied device to device, over NVLink where the
+ * GPUs are peers); num_kmers, k and the rest of the reference's fields are kept. */
+hash_set *tb_set_clone(const hash_set *src, int device);
+/* Testing aid (no GPU): the host pipeline -- reader, batches, n_workers stand-ins for the device
+ * workers, router, the three writers, TSV -- with record i assigned to bins[i % n_bins]. */
+int tb_route_fastx(const char *reads_path, const char *bins, int64_t n_bins, int gzip_output, int gzip_level,
+                   int fastq_encoder, int n_workers, int round_robin, int py_text_mode, int64_t py_buffer_size,
+                   const char *out_a, const char *out_b, const char *out_u, int tsv_fd, int64_t batch_bases,
+                   int n_threads, tb_stream_stats *stats);
 int tb_classify_fastx(const char *reads_path, const hash_set *A, const hash_set *B,
                       const char *out_a, const char *out_b, const char *out_u, int gzip_level,
                       int tsv_fd, int64_t batch_bases, int n_threads, tb_stream_stats *stats);

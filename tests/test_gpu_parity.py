@@ -494,9 +494,11 @@ def _write_fastq(path, bases, offsets, rng, width=0):
 
 
 def test_native_pipeline_equals_python_io(kmers, capsys, tmp_path):
-    """Same input through the native pipeline (default), the Python reader/writer (--python-io)
-    and the native pipeline with its FASTQ-aware gzip encoder (--fastq-gzip): identical TSV and
-    identical decompressed outputs, several batches."""
+    """Same input through the native pipeline (default: 2-bit batches, every visible GPU, FASTQ-aware
+    gzip encoder), the same with zlib only, forced onto one GPU and onto two workers' worth of
+    devices, and the Python reader/writer (--python-io) -- in gzip and in plain mode (the
+    reference's --no-gzip-output with its two-handles artefact, seq.py:127-130): identical TSV and
+    identical (decompressed) outputs, several batches."""
     import random
 
     from trio_binning_b200 import synth
@@ -510,27 +512,55 @@ def test_native_pipeline_equals_python_io(kmers, capsys, tmp_path):
     synth.write_kmer_file(str(pb), kb, k)
     reads = tmp_path / "reads.fastq.gz"
     _write_fastq(reads, bases, offsets, random.Random(3))
-    outs = {}
-    for mode, extra in (("native", []), ("python", ["--python-io"]), ("native_fastq_gzip", ["--fastq-gzip"])):
-        d = tmp_path / mode
-        d.mkdir()
-        argv = ["classify-by-kmers", str(reads), str(pa), str(pb), "--haplotype-a-out-prefix", str(d / "A"),
-                "--haplotype-b-out-prefix", str(d / "B"), "--unclassified-out-prefix", str(d / "U"),
-                "--batch-bases", "100000"] + extra
-        with patch("sys.argv", argv):
-            main()
-        tsv, _ = capsys.readouterr()
-        files = {n: gzip.decompress(open(d / n, "rb").read()) for n in sorted(os.listdir(d))}
-        outs[mode] = (tsv, files)
-    assert sorted(outs["native"][1]) == ["A.fastq.gz", "B.fastq.gz", "U.fastq.gz"]
-    assert outs["native"][0] == outs["python"][0]
-    assert outs["native"][1] == outs["python"][1]
-    # the FASTQ-aware gzip encoder changes the compressed bytes only
-    assert outs["native_fastq_gzip"] == outs["python"]
-    assert "TB_FASTQ_GZIP" not in os.environ
-    assert outs["native"][0].count("\n") == 600
-    bins = [line.split("\t")[1] for line in outs["native"][0].splitlines()]
-    assert {"A", "B", "U"} <= set(bins)
+    for plain in (False, True):
+        outs = {}
+        for mode, extra in (("native", []), ("python", ["--python-io"]), ("native_zlib", ["--no-fastq-gzip"]),
+                            ("native_1gpu", ["--gpus", "1"]), ("native_2gpu", ["--gpus", "2"])):
+            d = tmp_path / f"{mode}_{plain}"
+            d.mkdir()
+            argv = ["classify-by-kmers", str(reads), str(pa), str(pb), "--haplotype-a-out-prefix", str(d / "A"),
+                    "--haplotype-b-out-prefix", str(d / "B"), "--unclassified-out-prefix", str(d / "U"),
+                    "--batch-bases", "100000"] + extra + (["--no-gzip-output"] if plain else [])
+            with patch("sys.argv", argv):
+                main()
+            tsv, _ = capsys.readouterr()
+            files = {n: (open(d / n, "rb").read() if plain else gzip.decompress(open(d / n, "rb").read()))
+                     for n in sorted(os.listdir(d))}
+            outs[mode] = (tsv, files)
+        assert sorted(outs["native"][1]) == (["A.fastq", "U.fastq"] if plain else ["A.fastq.gz", "B.fastq.gz", "U.fastq.gz"])
+        for mode in outs:
+            assert outs[mode][0] == outs["python"][0], (mode, plain)
+            assert outs[mode][1] == outs["python"][1], (mode, plain)
+        assert outs["native"][0].count("\n") == 600
+        bins = [line.split("\t")[1] for line in outs["native"][0].splitlines()]
+        assert {"A", "B", "U"} <= set(bins)
+
+
+def test_set_clone_is_a_replica(kmers, oracle):
+    """tb_set_clone (the per-GPU replicas of the one-process multi-GPU pipeline): same membership,
+    same reference-visible fields, independent lifetime.  Cloned onto the last visible device (the
+    same one on a single-GPU box)."""
+    from trio_binning_b200 import synth
+
+    k = 21
+    ka, kb = synth.random_kmer_sets(50_000, 40_000, k, seed=31)
+    A, B = kmers.create_kmer_hash_set_from_ints(ka, k), kmers.create_kmer_hash_set_from_ints(kb, k)
+    dev = kmers.device_count() - 1
+    A2, B2 = kmers.clone_kmer_hash_set(A, dev), kmers.clone_kmer_hash_set(B, dev)
+    assert A2.contents.device == dev and A2.contents.num_kmers == len(ka) and A2.contents.k == k
+    assert A2.contents.n_distinct == A.contents.n_distinct and A2.contents.d_table != A.contents.d_table
+    bases, offsets, _ = synth.random_reads(300, 2000, k, ka, kb, seed=32, plant_every=150, invalid_rate=0.001)
+    want = kmers.classify_packed(bases, offsets, A, B)
+    kmers.destroy_kmer_hash_set(A)
+    kmers.destroy_kmer_hash_set(B)
+    got = kmers.classify_packed(bases, offsets, A2, B2)
+    for w, g in zip(want, got):
+        assert (w == g).all()
+    oa, ob = _oracle_sets(oracle, ka, kb, k)
+    wa, wb = oracle.count_batch(bases, offsets, oa, ob)
+    assert (got[0] == wa).all() and (got[1] == wb).all()
+    kmers.destroy_kmer_hash_set(A2)
+    kmers.destroy_kmer_hash_set(B2)
 
 
 # ---------------------------------------------------------------- the reference's own binding

@@ -1,0 +1,143 @@
+"""The host side of the native pipeline without a GPU (tb_route_fastx: the product's reader,
+batches, worker threads, in-order router, writers and TSV; the classifier is replaced by a
+fixed pattern of bins).  What must hold, against the Python writer that mirrors the reference
+(trio_binning_b200/seq.py == reference seq.py:98-136 + Read.print :33-42):
+
+  * any number of workers, either dealing mode, any batch size -> byte-identical outputs
+    (the multi-GPU merge logic; reference loop classify_by_kmers.py:99-117 is sequential);
+  * gzip mode: the decompressed bytes equal the reference writer's;
+  * plain mode (--no-gzip-output): hapA's file, written through TWO handles upstream
+    (seq.py:129), and the unclassified file are byte-identical to what CPython's buffered text
+    writers produce, for record sizes on both sides of every buffer threshold.
+"""
+import gzip
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def kmers():
+    from trio_binning_b200 import kmers as mod
+
+    return mod
+
+
+@pytest.fixture(scope="module")
+def seq():
+    from trio_binning_b200 import seq as mod
+
+    return mod
+
+
+def _fastx(path, lengths, seed, fasta_every=0, gz=False):
+    """Reads of the given lengths, FASTQ (FASTA for every `fasta_every`-th), names with a comment."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for i, n in enumerate(lengths):
+        s = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), n).tobytes()
+        if fasta_every and i % fasta_every == 0:
+            parts.append(b">f%d fasta record\n" % i + s + b"\n")
+        else:
+            q = rng.integers(33, 74, n, dtype=np.uint8).tobytes()
+            parts.append(b"@r%d/ccs np=%d\n" % (i, i % 7) + s + b"\n+\n" + q + b"\n")
+    data = b"".join(parts)
+    with (gzip.open(path, "wb", compresslevel=1) if gz else open(path, "wb")) as f:
+        f.write(data)
+    return len(lengths)
+
+
+def _python_writer(seq, reads_path, bins, tmp, gzip_output, ext):
+    """What the reference's loop writes for a given assignment of bins."""
+    d = os.path.join(tmp, "py")
+    os.makedirs(d, exist_ok=True)
+    fa, fb, fu = seq.open_outfiles(os.path.join(d, "hapA"), os.path.join(d, "hapB"), os.path.join(d, "hapU"), ext,
+                                   gzip_output)
+    tsv = []
+    for i, read in enumerate(seq.open_fastx_read(reads_path)):
+        b = bins[i % len(bins)]
+        read.print(file={"A": fa, "B": fb}.get(b, fu))
+        n = len(read.seq)
+        tsv.append("\t".join(map(str, [read.name, b, (n % 7) * 1.5, (n % 5) / 3.0])))
+    fa.close()
+    fb.close()
+    fu.close()
+    return d, "\n".join(tsv) + ("\n" if tsv else "")
+
+
+def _native(kmers, reads_path, bins, tmp, tag, gzip_output, ext, **kw):
+    d = os.path.join(tmp, tag)
+    os.makedirs(d, exist_ok=True)
+    suffix = ext + (".gz" if gzip_output else "")
+    tsv_path = os.path.join(d, "out.tsv")
+    with open(tsv_path, "wb") as t:
+        stats = kmers.route_fastx_file(reads_path, bins, os.path.join(d, "hapA" + suffix), os.path.join(d, "hapB" + suffix),
+                                       os.path.join(d, "hapU" + suffix), tsv_fd=t.fileno(), gzip_output=gzip_output, **kw)
+    return d, open(tsv_path).read(), stats
+
+
+def _content(path, gz):
+    raw = open(path, "rb").read()
+    return gzip.decompress(raw) if gz else raw
+
+
+LONG = [20_000, 9_000, 14_000, 40_000, 100, 8_191, 8_192, 8_193, 4_095, 4_096, 4_097, 25_000, 1, 3_000] * 3
+SHORT = [150] * 400 + [151, 149, 1, 2] * 10
+MIXED = [n for pair in zip(LONG, itertools.cycle([150, 4000, 60])) for n in pair]
+
+
+@pytest.mark.parametrize("shape,lengths", [("long", LONG), ("short", SHORT), ("mixed", MIXED)])
+@pytest.mark.parametrize("bins", ["ABU", "AB", "BAAB", "A", "B", "UUBUA", "ABBBBBBBBA"])
+def test_plain_output_equals_cpythons_writers(kmers, seq, tmp_path, shape, lengths, bins):
+    """The reference's --no-gzip-output mode incl. its two-handles-on-one-file artefact."""
+    tmp = str(tmp_path)
+    reads = os.path.join(tmp, "reads.fastq")
+    n = _fastx(reads, lengths, seed=len(bins) * 100 + len(lengths), fasta_every=5)
+    want_dir, want_tsv = _python_writer(seq, reads, bins, tmp, False, ".fastq")
+    got_dir, got_tsv, stats = _native(kmers, reads, bins, tmp, "native", False, ".fastq", batch_bases=50_000)
+    assert stats["n_reads"] == n
+    assert sorted(os.listdir(want_dir)) == ["hapA.fastq", "hapU.fastq"]  # upstream never creates hapB's file
+    assert sorted(f for f in os.listdir(got_dir) if f != "out.tsv") == ["hapA.fastq", "hapU.fastq"]
+    for name in ("hapA.fastq", "hapU.fastq"):
+        assert _content(os.path.join(got_dir, name), False) == _content(os.path.join(want_dir, name), False), name
+    assert got_tsv == want_tsv
+
+
+@pytest.mark.parametrize("workers,round_robin,batch", [(1, False, 1 << 20), (3, False, 30_000), (4, True, 30_000),
+                                                       (2, True, 1), (8, False, 5_000)])
+def test_outputs_do_not_depend_on_workers_or_batches(kmers, seq, tmp_path, workers, round_robin, batch):
+    tmp = str(tmp_path)
+    reads = os.path.join(tmp, "reads.fq.gz")
+    n = _fastx(reads, MIXED, seed=7, fasta_every=9, gz=True)
+    bins = "ABUUABBAUB"
+    want_dir, want_tsv = _python_writer(seq, reads, bins, tmp, True, ".fq")
+    for gz_out in (True, False):
+        ext = ".fq"
+        if not gz_out:
+            want_dir, _ = _python_writer(seq, reads, bins, os.path.join(tmp, "plain"), False, ext)
+        for encoder in ((True, False) if gz_out else (True,)):
+            got_dir, got_tsv, stats = _native(kmers, reads, bins, tmp, f"n_{gz_out}_{encoder}", gz_out, ext, workers=workers,
+                                              round_robin=round_robin, batch_bases=batch, fastq_encoder=encoder,
+                                              gzip_level=1)
+            assert stats["n_reads"] == n and got_tsv == want_tsv
+            assert stats["devices_used"] >= 1 and (not round_robin or stats["devices_used"] == min(workers, stats["n_batches"]))
+            names = ["hapA", "hapB", "hapU"] if gz_out else ["hapA", "hapU"]
+            for name in names:
+                suffix = ext + (".gz" if gz_out else "")
+                assert _content(os.path.join(got_dir, name + suffix), gz_out) == \
+                    _content(os.path.join(want_dir, name + suffix), gz_out), (name, gz_out, encoder)
+
+
+def test_empty_input_and_single_record(kmers, seq, tmp_path):
+    tmp = str(tmp_path)
+    for tag, data in (("empty", b""), ("one", b">only\nACGT\n"), ("no_newline", b"@q\nACGT\n+\n!!!!")):
+        reads = os.path.join(tmp, f"{tag}.fa")
+        open(reads, "wb").write(data)
+        for gz_out in (True, False):
+            want_dir, want_tsv = _python_writer(seq, reads, "B", os.path.join(tmp, f"{tag}{gz_out}"), gz_out, ".fa")
+            got_dir, got_tsv, _ = _native(kmers, reads, "B", os.path.join(tmp, f"{tag}{gz_out}"), "native", gz_out, ".fa", workers=2)
+            assert got_tsv == want_tsv
+            for f in os.listdir(want_dir):
+                assert _content(os.path.join(got_dir, f), gz_out) == _content(os.path.join(want_dir, f), gz_out), (tag, f)

@@ -6,11 +6,12 @@ based on the presence of k-mers.
 # Host-side mirror of the reference driver (reference
 # src/trio_binning/classify_by_kmers.py): same command line (:14-54), same
 # scaling factors (:57-77), same three output files and the same TSV on stdout
-# (:99-117).  The per-read ctypes call of the reference's loop is replaced by
-# batches: reads are gathered until a batch holds --batch-bases bases, the batch
-# is counted and decided (A/B/U, fp64) on the GPU, and records/TSV lines are
-# written in input order.  Launched under torchrun, batches are dealt round-robin
-# to one process per GPU (sharding.py) and rank 0 writes everything in input order.
+# (:99-117).  The per-read ctypes call of the reference's loop is replaced by the
+# native pipeline (csrc/fastx_pipeline.cpp): one process parses the reads once,
+# packs them to 2 bits, deals batches to one worker thread per GPU (each GPU holds
+# its own replica of the two sets), and writes records and TSV lines in input
+# order -- gzip or plain, whatever the reference's flags ask for.  --python-io keeps
+# the reference's own reader/writer code path (seq.py) around the batched GPU call.
 
 import argparse
 import os
@@ -18,7 +19,7 @@ import sys
 from os import path
 from typing import Tuple
 
-from . import kmers, seq, sharding
+from . import kmers, seq
 
 DEFAULT_BATCH_BASES = 256 << 20
 
@@ -41,17 +42,22 @@ _B200_ARGUMENTS = (
                               help="bases per GPU batch (B200 addition; does not change results)")),
     (("--python-io",), dict(action="store_true", default=False,
                             help="read and write FASTA/FASTQ in Python like the reference instead of the "
-                                 "native multi-threaded pipeline (B200 addition; same output)")),
+                                 "native multi-threaded pipeline (B200 addition; same output, one GPU)")),
+    (("--gpus",), dict(type=int, default=0,
+                       help="number of GPUs to spread the batches over, 0 = all visible ones; the sets are "
+                            "replicated on each, the output does not depend on it (B200 addition)")),
     (("--gzip-level",), dict(type=int, default=6,
-                             help="compression level of the gzipped outputs: 6 costs a fraction of the time "
-                                  "of 9, the level the reference's gzip.open uses, for files about 0.5 percent "
-                                  "larger; the decompressed bytes are the same at any level (B200 addition; "
-                                  "native pipeline only)")),
+                             help="zlib level for output chunks the FASTQ-aware encoder declines (short reads) "
+                                  "or for everything with --no-fastq-gzip: 6 costs a fraction of the time of 9, "
+                                  "the level the reference's gzip.open uses, for files about 0.5 percent larger; "
+                                  "the decompressed bytes are the same at any level (B200 addition)")),
+    (("--no-fastq-gzip",), dict(action="store_true", default=False,
+                                help="compress the outputs with zlib only. By default long-read chunks go through "
+                                     "the FASTQ-aware gzip encoder: standard gzip files, smaller than zlib level 9 "
+                                     "on long reads and many times faster; every block is decoded and compared "
+                                     "before it is written (B200 addition)")),
     (("--fastq-gzip",), dict(action="store_true", default=False,
-                             help="compress the outputs with the FASTQ-aware gzip encoder instead of zlib: "
-                                  "standard gzip files, smaller than level 9 on long reads and many times "
-                                  "faster; every block is decoded and compared before it is written "
-                                  "(B200 addition; native pipeline only)")),
+                             help="(default since round 2; kept so that old command lines still parse)")),
     (("--threads",), dict(type=int, default=0,
                           help="host threads for the native pipeline, 0 = all cores (B200 addition)")),
 )
@@ -91,11 +97,17 @@ def _emit(read, result, files, out):
 
 
 def _main_native(args):
-    """gzip outputs on one GPU: the whole loop (parse, batch, classify, route, compress, TSV)
-    runs in the native pipeline (csrc/fastx_pipeline.cpp); file names follow the reference."""
+    """The whole loop (parse, pack, classify on every GPU, route, compress or write plain, TSV)
+    in the native pipeline; file names follow the reference (:90 and seq.py:122-134)."""
     extension = path.splitext(args.reads.rstrip(".gz"))[1]  # reference :90 (quirk Q8)
-    names = [prefix + extension + ".gz" for prefix in
+    suffix = extension + ("" if args.no_gzip_output else ".gz")
+    names = [prefix + suffix for prefix in
              (args.haplotype_a_out_prefix, args.haplotype_b_out_prefix, args.unclassified_out_prefix)]
+    n_gpus = kmers.device_count() if args.gpus <= 0 else min(args.gpus, kmers.device_count())
+    first = kmers.lib.tb_get_device()
+    devices = [first] + [d for d in range(kmers.device_count()) if d != first][: n_gpus - 1]
+    sets_a = [args.haplotype_a_kmers] + [kmers.clone_kmer_hash_set(args.haplotype_a_kmers, d) for d in devices[1:]]
+    sets_b = [args.haplotype_b_kmers] + [kmers.clone_kmer_hash_set(args.haplotype_b_kmers, d) for d in devices[1:]]
     sys.stdout.flush()
     try:
         fd = sys.stdout.fileno()
@@ -106,20 +118,14 @@ def _main_native(args):
 
         borrowed = tempfile.TemporaryFile()
         fd = borrowed.fileno()
-    previous = os.environ.get("TB_FASTQ_GZIP")
-    if args.fastq_gzip:
-        os.environ["TB_FASTQ_GZIP"] = "1"  # read by tb_classify_fastx when it sets up its writers
     try:
-        stats = kmers.classify_fastx_file(args.reads, args.haplotype_a_kmers, args.haplotype_b_kmers,
-                                          names[0], names[1], names[2], tsv_fd=fd,
+        stats = kmers.classify_fastx_file(args.reads, sets_a, sets_b, names[0], names[1], names[2], tsv_fd=fd,
                                           gzip_level=args.gzip_level, batch_bases=args.batch_bases,
-                                          threads=args.threads)
+                                          threads=args.threads, gzip_output=not args.no_gzip_output,
+                                          fastq_encoder=not args.no_fastq_gzip)
     finally:
-        if args.fastq_gzip:
-            if previous is None:
-                os.environ.pop("TB_FASTQ_GZIP", None)
-            else:
-                os.environ["TB_FASTQ_GZIP"] = previous
+        for replica in sets_a[1:] + sets_b[1:]:
+            kmers.destroy_kmer_hash_set(replica)
     if os.environ.get("TB_VERBOSE"):
         print("[tb] native pipeline: " + ", ".join(f"{k}={v:.3f}" if isinstance(v, float) else f"{k}={v}"
                                                    for k, v in stats.items()), file=sys.stderr)
@@ -130,34 +136,45 @@ def _main_native(args):
     return stats
 
 
+def _batches(reads, batch_bases):
+    """Consecutive reads until a batch holds batch_bases bases."""
+    batch, total = [], 0
+    for read in reads:
+        batch.append(read)
+        total += len(read.seq)
+        if total >= batch_bases:
+            yield batch
+            batch, total = [], 0
+    if batch:
+        yield batch
+
+
 def main(argv=None):
     """Main method of program"""
-    # Under torchrun (WORLD_SIZE > 1) every rank drives its own GPU; the sets are built
-    # while the arguments are parsed, so the device has to be chosen first.
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
-        kmers.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    comm = sharding.Communicator.from_env()
+    # One process drives every GPU.  Started under torchrun (one process per GPU) only rank 0
+    # works -- the others would just parse the same file again.
+    if int(os.environ.get("RANK", "0")) != 0:
+        print("classify-by-kmers: one process drives all GPUs; rank "
+              f"{os.environ['RANK']} has nothing to do", file=sys.stderr)
+        return
 
     args = parse_args(argv)
 
-    if not args.no_gzip_output and not args.python_io and comm.world == 1:
+    if not args.python_io:
         _main_native(args)
         return
 
     reads = seq.open_fastx_read(args.reads)
 
-    file_a = file_b = file_u = None
-    if comm.rank == 0:
-        # three locals, released in this order when main() returns, like the reference's
-        file_a, file_b, file_u = seq.open_outfiles(
-            args.haplotype_a_out_prefix,
-            args.haplotype_b_out_prefix,
-            args.unclassified_out_prefix,
-            # reference :90 -- rstrip strips a CHARACTER SET, kept as is (quirk Q8)
-            path.splitext(args.reads.rstrip(".gz"))[1],
-            not args.no_gzip_output,
-        )
+    # three locals, released in this order when main() returns, like the reference's
+    file_a, file_b, file_u = seq.open_outfiles(
+        args.haplotype_a_out_prefix,
+        args.haplotype_b_out_prefix,
+        args.unclassified_out_prefix,
+        # reference :90 -- rstrip strips a CHARACTER SET, kept as is (quirk Q8)
+        path.splitext(args.reads.rstrip(".gz"))[1],
+        not args.no_gzip_output,
+    )
 
     # The device computes count * scaling in fp64 with the same factors
     # (tb_scaling_factors); this call is kept for API parity and as a cross-check.
@@ -165,13 +182,10 @@ def main(argv=None):
     assert (scaling_a, scaling_b) == kmers.scaling_factors(args.haplotype_a_kmers, args.haplotype_b_kmers)
 
     set_a, set_b = args.haplotype_a_kmers, args.haplotype_b_kmers
-    sharding.run_sharded(
-        reads,
-        classify_fn=lambda seqs: kmers.classify_reads(seqs, set_a, set_b),
-        emit_fn=lambda read, result: _emit(read, result, (file_a, file_b, file_u), sys.stdout),
-        batch_bases=args.batch_bases,
-        comm=comm,
-    )
+    for batch in _batches(reads, args.batch_bases):
+        results = kmers.classify_reads([read.seq for read in batch], set_a, set_b)
+        for read, result in zip(batch, results):
+            _emit(read, result, (file_a, file_b, file_u), sys.stdout)
 
 
 if __name__ == "__main__":

@@ -636,6 +636,36 @@ hash_set *tb_set_create_from_keys(const uint64_t *keys, uint64_t n, int k, int d
     return s;
 }
 
+hash_set *tb_set_clone(const hash_set *src, int device)
+{
+    if (!valid_set(src)) { fail("invalid set handle"); return NULL; }
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (use_device(device)) return NULL;
+    hash_set *s = (hash_set *)malloc(sizeof(hash_set));
+    *s = *src;
+    s->device = device;
+    s->d_table = NULL;
+    const size_t bytes = (size_t)src->n_buckets * sizeof(tb_bucket);
+    cudaError_t e = cudaMalloc((void **)&s->d_table, bytes);
+    if (e == cudaSuccess) {
+        if (device != src->device) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, device, src->device);
+            if (can && cudaDeviceEnablePeerAccess(src->device, 0) == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        }
+        e = cudaMemcpyPeer(s->d_table, device, src->d_table, src->device, bytes);
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        fail("cloning a set to device %d failed: %s", device, cudaGetErrorString(e));
+        if (s->d_table) cudaFree(s->d_table);
+        free(s);
+        cudaGetLastError();
+        return NULL;
+    }
+    return s;
+}
+
 void tb_set_destroy(hash_set *s)
 {
     if (!valid_set(s)) return;

@@ -696,7 +696,19 @@ __device__ __forceinline__ uint32_t ld_filter_l1(const uint32_t *p, uint64_t pol
     // allocate in L1 (the next windows re-read this sector), keep in L2; a 64-B L2 fetch
     // granularity (L2::64B) was measured and changes nothing here
     uint32_t v;
+#if !defined(TB_BITMAP_LD) || TB_BITMAP_LD == 0
     asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+#elif TB_BITMAP_LD == 1  // measurement variants (tools/variants.sh)
+    asm volatile("ld.global.nc.L2::cache_hint.L2::64B.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+#elif TB_BITMAP_LD == 2
+    asm volatile("ld.global.nc.L2::cache_hint.L2::128B.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+#elif TB_BITMAP_LD == 3
+    (void)policy;
+    asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p));
+#else
+    (void)policy;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+#endif
     return v;
 }
 

@@ -5,17 +5,19 @@
 //                   -> FASTA/FASTQ records with the exact semantics of the reference's
 //                   readfq (src/trio_binning/seq.py:45-83, quirk Q7) -> batches whose
 //                   sequences are concatenated straight into pinned memory
-//   main thread   : batch -> tb_classifier_submit on one of n slots (H2D + kernels + D2H
-//                   overlap the parsing of the next batches) -> wait -> route every record
-//                   to its bin (classify_by_kmers.py:104-115) -> TSV line (:117)
+//   packer thread : batch -> pinned 2-bit arrays (tb_pack_reads): 0.25 byte per base crosses PCIe
+//   device workers: one thread per GPU, two slots each, every GPU with its own replica of the
+//                   sets: tb_classifier_submit_packed (H2D + kernels + D2H overlap the parsing
+//                   and packing of the next batches) -> wait
+//   router        : completed batches back into input order -> every record to its bin
+//                   (classify_by_kmers.py:104-115) -> TSV line (:117)
 //   deflate pool  : each bin's text is cut into chunks that are compressed in parallel as
 //                   independent gzip members and written in order (a concatenation of
 //                   members is a valid .gz; the DECOMPRESSED bytes equal the reference's
 //                   gzip.open(..., "wt") output, seq.py:132-134)
-//
-// Only gzip output is handled natively; --no-gzip-output keeps the Python writer because
-// the reference's plain mode depends on Python's buffered-writer behaviour (two handles on
-// one file, seq.py:129).
+//   plain output  : the reference's --no-gzip-output mode, CPython's buffered text writers
+//                   restated so that the two handles the reference opens on hapA's file
+//                   (seq.py:129) overwrite each other exactly as they do upstream.
 #include <fcntl.h>
 #include <errno.h>
 #include <stdint.h>
@@ -28,7 +30,11 @@
 #include "fastq_deflate.h"
 #include "gz_stream.h"
 
+#include <sys/stat.h>
+
 #include <algorithm>
+#include <atomic>
+#include <map>
 #include <charconv>
 #include <chrono>
 #include <condition_variable>
@@ -117,6 +123,8 @@ public:
         }
     }
     uint64_t bytes_in() const { return bytes_in_; }
+    // time spent inside the inflate (summed over the decoding threads; 0 for plain input)
+    double inflate_seconds() const { return (double)inflate_ns_.load() * 1e-9; }
     const std::string &error() const { return error_; }
     bool parallel_bgzf() const { return bgzf_ && decode_threads_ > 1; }
 
@@ -207,7 +215,9 @@ private:
             c->data.resize(kChunkBytes);
             long got;
             if (gz_) {
+                const auto t0 = Clock::now();
                 got = gzs_.read(c->data.data(), c->data.size());
+                inflate_ns_.fetch_add((uint64_t)(seconds_since(t0) * 1e9));
                 bytes_in_ = bgzf_bytes_ + gzs_.compressed_bytes();
             } else {
                 do got = (long)::read(fd_, c->data.data(), c->data.size());
@@ -313,6 +323,7 @@ private:
                 c->why = "out of memory while decoding BGZF blocks";
             }
             gz.open_memory(c->comp.data(), c->comp.size());
+            const auto t_dec = Clock::now();
             while (!bad) {
                 // one spare byte of room shows an overlong stream instead of truncating it
                 char extra;
@@ -326,6 +337,7 @@ private:
                 bad = true;
                 c->why = "corrupt gzip input: BGZF block shorter than its ISIZE";
             }
+            inflate_ns_.fetch_add((uint64_t)(seconds_since(t_dec) * 1e9));
             c->len = n;
             c->failed = bad;
             finish(c);
@@ -394,6 +406,7 @@ private:
     const char *cur_ = nullptr;
     size_t pos_ = 0, len_ = 0;
     uint64_t bytes_in_ = 0, bgzf_bytes_ = 0;
+    std::atomic<uint64_t> inflate_ns_{ 0 };
     std::string error_;
 };
 
@@ -427,7 +440,10 @@ struct Rec {
 };
 
 struct Batch {
-    bool pinned = true;     // page-locked (GPU pipeline) or plain malloc (parser-only use)
+    bool pinned = true;     // sequences in page-locked memory, or plain malloc (they stay on the host)
+    bool pinned_results = true;
+    void *owner = nullptr;  // the pipeline's wrapper around this batch
+    uint64_t first_record = 0;  // index of the batch's first record in the input
     char *bases = nullptr;
     int64_t cap_bases = 0;
     std::vector<int64_t> offsets;  // n+1
@@ -450,21 +466,21 @@ struct Batch {
         text.clear();
         last = false;
     }
-    void *alloc(uint64_t n) { return pinned ? tb_host_alloc(n) : malloc(n ? n : 1); }
-    void release(void *p)
+    void *alloc(uint64_t n, bool pin) { return pin ? tb_host_alloc(n) : malloc(n ? n : 1); }
+    void release(void *p, bool pin)
     {
         if (!p) return;
-        if (pinned) tb_host_free(p); else free(p);
+        if (pin) tb_host_free(p); else free(p);
     }
     // make room for `need` bytes, keeping the first `used` bytes
     bool grow_bases(int64_t need, int64_t used = 0)
     {
         int64_t cap = std::max<int64_t>(need + need / 4, 1 << 20);
-        char *nb = (char *)alloc((uint64_t)cap);
+        char *nb = (char *)alloc((uint64_t)cap, pinned);
         if (!nb) return false;
         if (bases) {
             memcpy(nb, bases, (size_t)used);
-            release(bases);
+            release(bases, pinned);
         }
         bases = nb;
         cap_bases = cap;
@@ -475,20 +491,21 @@ struct Batch {
         if (n_reads <= cap_reads) return true;
         free_results();
         cap_reads = n_reads + n_reads / 4 + 1024;
-        ca = (int32_t *)alloc((uint64_t)cap_reads * 4);
-        cb = (int32_t *)alloc((uint64_t)cap_reads * 4);
-        sa = (double *)alloc((uint64_t)cap_reads * 8);
-        sb = (double *)alloc((uint64_t)cap_reads * 8);
-        bin = (char *)alloc((uint64_t)cap_reads);
+        const bool pin = pinned_results;
+        ca = (int32_t *)alloc((uint64_t)cap_reads * 4, pin);
+        cb = (int32_t *)alloc((uint64_t)cap_reads * 4, pin);
+        sa = (double *)alloc((uint64_t)cap_reads * 8, pin);
+        sb = (double *)alloc((uint64_t)cap_reads * 8, pin);
+        bin = (char *)alloc((uint64_t)cap_reads, pin);
         return ca && cb && sa && sb && bin;
     }
     void free_results()
     {
-        release(ca);
-        release(cb);
-        release(sa);
-        release(sb);
-        release(bin);
+        release(ca, pinned_results);
+        release(cb, pinned_results);
+        release(sa, pinned_results);
+        release(sb, pinned_results);
+        release(bin, pinned_results);
         ca = cb = nullptr;
         sa = sb = nullptr;
         bin = nullptr;
@@ -497,7 +514,7 @@ struct Batch {
     ~Batch()
     {
         free_results();
-        release(bases);
+        release(bases, pinned);
     }
 };
 
@@ -543,6 +560,7 @@ struct Reader {
         const auto t0 = Clock::now();
         cur = free_q->pop();
         cur->reset();
+        cur->first_record = 0;
         int64_t seq_start = 0;  // where the current record's sequence starts in cur->bases
         int64_t fill = 0;       // bytes of cur->bases in use (incl. the record being read)
 
@@ -567,6 +585,7 @@ struct Reader {
                 full_q->push(cur);
                 cur = free_q->pop();
                 cur->reset();
+                cur->first_record = n_reads;
                 fill = 0;
             }
         };
@@ -759,18 +778,33 @@ private:
     bool stop_ = false;
 };
 
-struct GzFileWriter {
+// ---------------------------------------------------------------------------------------
+// bin writers.  record() receives str(read) (seq.py:27-31) WITHOUT the newline print() adds:
+// Read.print() is print(self, file=f), i.e. f.write(str(self)) followed by f.write("\n") --
+// two writes, which matters for the plain-text writer below.
+// ---------------------------------------------------------------------------------------
+struct BinWriter {
+    virtual ~BinWriter() {}
+    virtual bool open(const std::string &path) = 0;
+    virtual void record(const char *text, size_t n) = 0;
+    virtual void drain(bool all) = 0;
+    virtual void finish() = 0;
+    uint64_t raw_bytes = 0, out_bytes = 0;
+    bool failed = false;
+};
+
+struct GzFileWriter : BinWriter {
     int fd = -1;
     int level = 9;
     bool fastq_encoder = false;  // try the FASTQ-aware encoder first, zlib where it declines
     Pool *pool = nullptr;
+    std::atomic<uint64_t> *deflate_ns = nullptr;  // CPU time spent compressing, summed over the pool
     std::string pending;  // uncompressed text not yet dispatched
     std::deque<std::shared_future<std::shared_ptr<std::string>>> inflight;
-    uint64_t raw_bytes = 0, gz_bytes = 0;
-    bool any_member = false, failed = false;
+    bool any_member = false;
     static constexpr size_t kChunk = 4 << 20;
 
-    bool open(const std::string &path)
+    bool open(const std::string &path) override
     {
         fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
         return fd >= 0;
@@ -783,10 +817,13 @@ struct GzFileWriter {
         inflight.push_back(prom->get_future().share());
         const int lvl = level;
         const bool fq = fastq_encoder;
-        pool->submit([in, prom, lvl, fq] {
+        std::atomic<uint64_t> *ns = deflate_ns;
+        pool->submit([in, prom, lvl, fq, ns] {
+            const auto t0 = Clock::now();
             auto out = std::make_shared<std::string>();
             if (!(fq && tb::fastq_gzip_member(in->data(), in->size(), *out, true)) && !gzip_member(*in, lvl, *out))
                 out->clear();
+            if (ns) ns->fetch_add((uint64_t)(seconds_since(t0) * 1e9));
             prom->set_value(out);
         });
         any_member = true;
@@ -805,8 +842,13 @@ struct GzFileWriter {
             }
         }
     }
+    void record(const char *text, size_t n) override
+    {
+        append(text, n);
+        append("\n", 1);
+    }
     // write whatever has finished compressing, in order; block for all if `all`
-    void drain(bool all)
+    void drain(bool all) override
     {
         while (!inflight.empty()) {
             auto &f = inflight.front();
@@ -819,11 +861,11 @@ struct GzFileWriter {
                 if (w <= 0) { failed = true; break; }
                 off += (size_t)w;
             }
-            gz_bytes += out->size();
+            out_bytes += out->size();
             inflight.pop_front();
         }
     }
-    void finish()
+    void finish() override
     {
         if (!pending.empty() || !any_member) {
             // Python always produces a valid (possibly empty) gzip file
@@ -836,76 +878,463 @@ struct GzFileWriter {
     }
 };
 
-}  // namespace
+// The reference's --no-gzip-output mode writes through open(name, "w") (seq.py:127-130): a
+// TextIOWrapper over a BufferedWriter over its own file descriptor.  Plain mode opens the B
+// handle on A's file name (seq.py:129), so two such objects, each with its own file position,
+// write over each other and WHEN each flushes decides the bytes that survive -- the reference's
+// own golden file (tests/data/hapA.fastq) is such an overlap.  This is CPython's (3.9 .. 3.12)
+// write path restated:
+//   TextIOWrapper.write(s): a pending list collects encoded strings and is flushed once it holds
+//     >= 8192 bytes (Modules/_io/textio.c, _io_TextIOWrapper_write_impl).  WHEN a list that is
+//     not empty is flushed before s joins it depends on the interpreter (text_mode, probed by the
+//     Python caller on the running interpreter): 0 = when s alone is >= 8192 bytes (CPython 3.9
+//     .. 3.12), 1 = when list + s would exceed 8192 bytes (later versions), 2 = never (3.8);
+//   BufferedWriter.write(b): b is copied into the buffer if it fits in what is left of it;
+//     otherwise the buffer is written out, then b itself goes straight to the descriptor while
+//     more than a buffer's worth remains (one write() takes all of it), and a short rest is
+//     buffered (Modules/_io/bufferedio.c, _io_BufferedWriter_write_impl);
+//   the buffer size is the file's st_blksize (io.open) unless the caller passes the size its
+//     interpreter uses;
+//   close() flushes the pending list, then the buffer.
+struct PyTextFileWriter : BinWriter {
+    int fd = -1;
+    static constexpr size_t kTextChunk = 8192;
+    std::string pending;
+    bool has_pending = false;
+    size_t pending_count = 0;
+    std::vector<char> buf;
+    size_t pos = 0;
+    int text_mode = 0;
+    size_t buffer_size = 0;  // 0: st_blksize
 
-extern "C" {
+    bool open(const std::string &path) override
+    {
+        fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        if (fd < 0) return false;
+        struct stat st;
+        size_t bs = 8192;
+        if (buffer_size > 0) bs = buffer_size;
+        else if (fstat(fd, &st) == 0 && st.st_blksize > 1) bs = (size_t)st.st_blksize;
+        buf.assign(bs, 0);
+        return true;
+    }
+    void raw_write(const char *p, size_t n)
+    {
+        out_bytes += n;
+        while (n > 0) {
+            const ssize_t w = ::write(fd, p, n);
+            if (w < 0 && errno == EINTR) continue;
+            if (w <= 0) { failed = true; return; }
+            p += w;
+            n -= (size_t)w;
+        }
+    }
+    void buffer_flush()
+    {
+        if (pos) raw_write(buf.data(), pos);
+        pos = 0;
+    }
+    void buffered_write(const char *p, size_t n)
+    {
+        if (n <= buf.size() - pos) {
+            memcpy(buf.data() + pos, p, n);
+            pos += n;
+            return;
+        }
+        buffer_flush();
+        if (n > buf.size()) {
+            raw_write(p, n);
+            return;
+        }
+        memcpy(buf.data(), p, n);
+        pos = n;
+    }
+    void text_flush()
+    {
+        if (!has_pending) return;
+        has_pending = false;
+        pending_count = 0;
+        buffered_write(pending.data(), pending.size());
+        pending.clear();
+    }
+    void text_write(const char *p, size_t n)
+    {
+        raw_bytes += n;
+        if (!has_pending) {
+            pending.assign(p, n);
+            has_pending = true;
+        } else if ((text_mode == 0 && n >= kTextChunk) || (text_mode == 1 && pending_count + n > kTextChunk)) {
+            text_flush();
+            pending.assign(p, n);
+            has_pending = true;
+        } else {
+            pending.append(p, n);
+        }
+        pending_count += n;
+        if (pending_count >= kTextChunk) text_flush();
+    }
+    void record(const char *text, size_t n) override
+    {
+        text_write(text, n);
+        text_write("\n", 1);
+    }
+    void drain(bool) override {}
+    void finish() override
+    {
+        text_flush();
+        buffer_flush();
+        if (fd >= 0) ::close(fd);
+        fd = -1;
+    }
+};
 
-int tb_classify_fastx(const char *reads_path, const hash_set *A, const hash_set *B,
-                      const char *out_a, const char *out_b, const char *out_u, int gzip_level,
-                      int tsv_fd, int64_t batch_bases, int n_threads, tb_stream_stats *stats)
+// ---------------------------------------------------------------------------------------
+// the pipeline
+//
+//   reader (1 thread)  file -> records -> Batch (sequences concatenated in ordinary host memory,
+//                      names/qualities beside them), batches numbered in input order
+//   packer (1 thread + the tb_pack_reads workers)  Batch -> pinned 2-bit arrays (F, dirty, the
+//                      rare fill-forward words, Q3-UB prefixes): what crosses PCIe is 0.25 byte
+//                      per base, never the ASCII
+//   device workers (1 thread per GPU, 2 slots each)  tb_classifier_submit_packed / wait on the
+//                      worker's own replica of the sets; batches are dealt on demand (a worker
+//                      takes the next batch when it has a free slot) or strictly round-robin
+//   router (calling thread)  completed batches back into input order -> every record to the
+//                      writer of its bin + one TSV line (classify_by_kmers.py:104-117)
+// ---------------------------------------------------------------------------------------
+struct PackedHost {
+    tb_packed_batch pb;
+    int64_t *offsets = nullptr;
+    int64_t cap_bases = -1, cap_reads = -1;
+    PackedHost() { memset(&pb, 0, sizeof pb); }
+    void release()
+    {
+        void *ptrs[] = { pb.F, pb.dirty, pb.dirty_idx, pb.e_words, pb.ub_read, pb.ub_skip, pb.ub_off, pb.ub_bytes, offsets };
+        for (void *p : ptrs)
+            if (p) tb_host_free(p);
+        memset(&pb, 0, sizeof pb);
+        offsets = nullptr;
+        cap_bases = cap_reads = -1;
+    }
+    bool ensure(int64_t total_bases, int64_t n_reads)
+    {
+        if (total_bases <= cap_bases && n_reads <= cap_reads) return true;
+        const int64_t nb = std::max(total_bases + total_bases / 8, cap_bases);
+        const int64_t nr = std::max(n_reads + n_reads / 8 + 64, cap_reads);
+        release();
+        const int64_t tiles = (nb + 1023) / 1024;
+        pb.cap_words = (tiles + 1) * 32;
+        pb.cap_tiles = tiles + 1;
+        pb.cap_dirty = pb.cap_words / 8 + 1024;  // more non-ACGT than that: the batch goes as ASCII
+        pb.cap_ub = nr + 1;
+        pb.cap_ub_bytes = std::max<int64_t>(1 << 20, nb / 16);
+        pb.F = (uint64_t *)tb_host_alloc((uint64_t)pb.cap_words * 8);
+        pb.dirty = (uint32_t *)tb_host_alloc((uint64_t)pb.cap_tiles * 4);
+        pb.dirty_idx = (uint32_t *)tb_host_alloc((uint64_t)pb.cap_dirty * 4);
+        pb.e_words = (uint64_t *)tb_host_alloc((uint64_t)pb.cap_dirty * 8);
+        pb.ub_read = (uint32_t *)tb_host_alloc((uint64_t)pb.cap_ub * 4);
+        pb.ub_skip = (uint32_t *)tb_host_alloc((uint64_t)pb.cap_ub * 4);
+        pb.ub_off = (int64_t *)tb_host_alloc((uint64_t)(pb.cap_ub + 1) * 8);
+        pb.ub_bytes = (unsigned char *)tb_host_alloc((uint64_t)pb.cap_ub_bytes);
+        offsets = (int64_t *)tb_host_alloc((uint64_t)(nr + 2) * 8);
+        if (!pb.F || !pb.dirty || !pb.dirty_idx || !pb.e_words || !pb.ub_read || !pb.ub_skip || !pb.ub_off ||
+            !pb.ub_bytes || !offsets) {
+            release();
+            return false;
+        }
+        cap_bases = nb;
+        cap_reads = nr;
+        return true;
+    }
+    ~PackedHost() { release(); }
+};
+
+struct PipeBatch {
+    Batch b;
+    PackedHost packed;
+    bool packed_ok = false;
+    uint64_t seq = 0;
+    bool failed = false;
+};
+
+template <class T>
+class Channel {
+public:
+    void push(T v)
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            q_.push_back(v);
+        }
+        cv_.notify_all();
+    }
+    T pop()
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return !q_.empty(); });
+        T v = q_.front();
+        q_.pop_front();
+        return v;
+    }
+    size_t size()
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        return q_.size();
+    }
+
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<T> q_;
+};
+
+struct PipelineConfig {
+    const char *reads_path = nullptr;
+    std::vector<const hash_set *> sets_a, sets_b;  // one replica per device
+    const char *stub_bins = nullptr;               // testing aid: no GPU, record i gets stub_bins[i % n]
+    int64_t n_stub = 0;
+    bool gzip_output = true;
+    int gzip_level = 6;
+    bool fastq_encoder = false;
+    bool round_robin = false;  // deal batch i to device i mod G instead of on demand
+    int py_text_mode = 0;      // plain output: which CPython's TextIOWrapper to restate
+    int64_t py_buffer_size = 0;  //             and its BufferedWriter's size (0: st_blksize)
+    int tsv_fd = -1;
+    int64_t batch_bases = 256 << 20;
+    int threads = 0;
+    std::string out_a, out_b, out_u;
+};
+
+int run_pipeline(const PipelineConfig &cfg, tb_stream_stats *stats)
 {
     const auto t_all = Clock::now();
-    if (!reads_path || !A || !B || !out_a || !out_b || !out_u) return -1;
-    if (batch_bases < 1) batch_bases = 1;
-    if (gzip_level < 0 || gzip_level > 9) gzip_level = 9;
-    int threads = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    const int n_dev = cfg.stub_bins ? std::max<int>(1, (int)cfg.sets_a.size()) : (int)cfg.sets_a.size();
+    if (n_dev < 1) return -1;
+    const int64_t batch_bases = std::max<int64_t>(1, cfg.batch_bases);
+    int threads = cfg.threads > 0 ? cfg.threads : (int)std::thread::hardware_concurrency();
     if (threads < 2) threads = 2;
-    const int n_slots = 2, n_batches = n_slots + 2;
+    const int n_slots = 2;
+    const int n_batches = n_dev * n_slots + 4;
+    const int k = cfg.stub_bins ? 21 : (int)cfg.sets_a[0]->k;
 
     Reader reader;
     reader.batch_bases = batch_bases;
     // a quarter of the host threads may decode BGZF blocks; the parser takes ~2 GB/s, which four
     // to six decoders fill
     reader.src.set_threads(std::max(1, std::min(6, threads / 4)));
-    if (!reader.src.open(reads_path, reader.error)) {
+    if (!reader.src.open(cfg.reads_path, reader.error)) {
         fprintf(stderr, "tb_classify_fastx: %s\n", reader.error.c_str());
+        tb_internal_set_error(reader.error.c_str());
         return -2;
     }
-    BatchQueue free_q, full_q;
+    BatchQueue free_q, parsed_q;
     reader.free_q = &free_q;
-    reader.full_q = &full_q;
-    std::vector<std::unique_ptr<Batch>> batches;
+    reader.full_q = &parsed_q;
+    std::vector<std::unique_ptr<PipeBatch>> batches;
     for (int i = 0; i < n_batches; i++) {
-        batches.emplace_back(new Batch());
-        if (!batches.back()->grow_bases(std::min<int64_t>(batch_bases, 64 << 20) + (1 << 20))) return -3;
-        free_q.push(batches.back().get());
+        batches.emplace_back(new PipeBatch());
+        Batch &b = batches.back()->b;
+        b.pinned = false;           // the ASCII stays on the host: ordinary memory
+        b.pinned_results = !cfg.stub_bins;
+        b.owner = batches.back().get();
+        if (!b.grow_bases(std::min<int64_t>(batch_bases, 64 << 20) + (1 << 20))) return -3;
+        free_q.push(&b);
     }
 
     Pool pool(std::max(1, threads - 1));
-    GzFileWriter wa, wb, wu;
-    // TB_FASTQ_GZIP=1 (CLI: --fastq-gzip): chunks of long-line text go through the FASTQ-aware
-    // encoder (fastq_deflate.cpp; smaller than zlib -9 on long reads at a fraction of the time,
-    // every member decoded and compared before it is written), everything else through zlib
-    const char *fq_env = getenv("TB_FASTQ_GZIP");
-    const bool fastq_encoder = fq_env && *fq_env && strcmp(fq_env, "0") != 0;
-    for (auto *w : { &wa, &wb, &wu }) {
-        w->pool = &pool;
-        w->level = gzip_level;
-        w->fastq_encoder = fastq_encoder;
+    std::atomic<uint64_t> deflate_ns{ 0 };
+    std::unique_ptr<BinWriter> wa, wb, wu;
+    if (cfg.gzip_output) {
+        for (auto *slot : { &wa, &wb, &wu }) {
+            auto *w = new GzFileWriter();
+            w->pool = &pool;
+            w->level = cfg.gzip_level;
+            w->fastq_encoder = cfg.fastq_encoder;
+            w->deflate_ns = &deflate_ns;
+            slot->reset(w);
+        }
+        if (!wa->open(cfg.out_a) || !wb->open(cfg.out_b) || !wu->open(cfg.out_u)) {
+            fprintf(stderr, "tb_classify_fastx: cannot create output files\n");
+            return -4;
+        }
+    } else {
+        for (auto *slot : { &wa, &wb, &wu }) {
+            auto *w = new PyTextFileWriter();
+            w->text_mode = cfg.py_text_mode;
+            w->buffer_size = cfg.py_buffer_size > 0 ? (size_t)cfg.py_buffer_size : 0;
+            slot->reset(w);
+        }
+        // seq.py:127-130: A, then B ON A's NAME (sic), then U -- each open() truncates
+        if (!wa->open(cfg.out_a) || !wb->open(cfg.out_a) || !wu->open(cfg.out_u)) {
+            fprintf(stderr, "tb_classify_fastx: cannot create output files\n");
+            return -4;
+        }
     }
-    if (!wa.open(out_a) || !wb.open(out_b) || !wu.open(out_u)) {
-        fprintf(stderr, "tb_classify_fastx: cannot create output files\n");
-        return -4;
-    }
+
+    std::atomic<int> rc{ 0 };
+    auto set_rc = [&](int v) { int z = 0; rc.compare_exchange_strong(z, v); };
+    std::mutex err_m;
+    std::string err_text;
+    auto set_err = [&](const char *what) {
+        std::lock_guard<std::mutex> lk(err_m);
+        if (err_text.empty()) err_text = what ? what : "";
+    };
 
     std::thread reader_thread([&] { reader.run(); });
 
-    tb_classifier *clf = nullptr;
-    int64_t clf_bases = 0, clf_reads = 0;
-    std::deque<Batch *> inflight;
-    std::string tsv, rec_text;
-    double gpu_wait_s = 0, write_s = 0;
-    uint64_t n_a = 0, n_b = 0, n_u = 0, n_batches_done = 0;
-    int rc = 0;
-    int next_slot = 0;
+    // ---- packer --------------------------------------------------------------------------
+    // per-device queues in round-robin mode, one shared queue otherwise
+    std::vector<std::unique_ptr<Channel<PipeBatch *>>> ready;
+    for (int d = 0; d < (cfg.round_robin ? n_dev : 1); d++) ready.emplace_back(new Channel<PipeBatch *>());
+    Channel<PipeBatch *> done_q;
+    double pack_s = 0;
+    const int pack_threads = std::max(1, std::min(16, threads / 2));
+    std::thread packer([&] {
+        uint64_t seq = 0;
+        for (;;) {
+            Batch *b = parsed_q.pop();
+            PipeBatch *pbatch = static_cast<PipeBatch *>(b->owner);
+            pbatch->seq = seq;
+            pbatch->failed = false;
+            pbatch->packed_ok = false;
+            const bool last = b->last;
+            if (!cfg.stub_bins && rc.load() == 0 && b->n() > 0) {
+                const auto t0 = Clock::now();
+                if (!pbatch->packed.ensure(b->total(), b->n())) {
+                    set_rc(-3);
+                    set_err("pinned allocation for a packed batch failed");
+                } else {
+                    memcpy(pbatch->packed.offsets, b->offsets.data(), (size_t)(b->n() + 1) * 8);
+                    const int prc = tb_pack_reads(b->bases, pbatch->packed.offsets, b->n(), k, pack_threads,
+                                                  &pbatch->packed.pb);
+                    pbatch->packed_ok = prc == 0;  // -3: too many non-ACGT words -> this batch goes as ASCII
+                    if (prc != 0 && prc != -3) {
+                        set_rc(-11);
+                        set_err("tb_pack_reads failed");
+                    }
+                }
+                pack_s += seconds_since(t0);
+            }
+            ready[cfg.round_robin ? (size_t)(seq % (uint64_t)n_dev) : 0]->push(pbatch);
+            seq++;
+            if (last) break;
+        }
+        for (auto &q : ready)
+            for (int d = 0; d < n_dev; d++) q->push(nullptr);  // one end marker per possible consumer
+    });
 
-    auto finish_batch = [&](Batch *b) {
-        auto t0 = Clock::now();
-        if (b->n() > 0 && tb_classifier_wait(clf, b->slot) != 0) rc = -5;
-        gpu_wait_s += seconds_since(t0);
-        t0 = Clock::now();
+    // ---- device workers --------------------------------------------------------------------
+    std::atomic<uint64_t> gpu_wait_ns{ 0 };
+    std::vector<int> used((size_t)n_dev, 0);
+    auto device_worker = [&](int d) {
+        Channel<PipeBatch *> &in = *ready[cfg.round_robin ? (size_t)d : 0];
+        tb_classifier *clf = nullptr;
+        int64_t clf_bases = 0, clf_reads = 0;
+        std::deque<PipeBatch *> inflight;
+        int next_slot = 0;
+        auto complete = [&](PipeBatch *p) {
+            const auto t0 = Clock::now();
+            if (!p->failed && tb_classifier_wait(clf, p->b.slot) != 0) {
+                set_rc(-5);
+                set_err(tb_last_error());
+                p->failed = true;
+            }
+            gpu_wait_ns.fetch_add((uint64_t)(seconds_since(t0) * 1e9));
+            done_q.push(p);
+        };
+        for (;;) {
+            PipeBatch *p = in.pop();
+            if (!p) break;
+            Batch &b = p->b;
+            if (cfg.stub_bins) {
+                // testing aid: bins from the caller's pattern, counts from the read lengths
+                if (b.n() > 0 && !b.ensure_results(b.n())) set_rc(-3);
+                for (int64_t r = 0; r < b.n() && rc.load() == 0; r++) {
+                    const int64_t len = b.offsets[(size_t)r + 1] - b.offsets[(size_t)r];
+                    b.ca[r] = (int32_t)(len % 7);
+                    b.cb[r] = (int32_t)(len % 5);
+                    b.sa[r] = b.ca[r] * 1.5;
+                    b.sb[r] = b.cb[r] / 3.0;
+                    b.bin[r] = cfg.stub_bins[(size_t)((b.first_record + (uint64_t)r) % (uint64_t)cfg.n_stub)];
+                }
+                used[(size_t)d] = 1;
+                done_q.push(p);
+                continue;
+            }
+            if (rc.load() != 0 || b.n() == 0) {
+                p->failed = rc.load() != 0;
+                // keep the order of completions of this worker: older batches first
+                while (!inflight.empty()) {
+                    complete(inflight.front());
+                    inflight.pop_front();
+                }
+                done_q.push(p);
+                continue;
+            }
+            used[(size_t)d] = 1;
+            if (!clf || b.total() > clf_bases || b.n() > clf_reads) {
+                while (!inflight.empty()) {
+                    complete(inflight.front());
+                    inflight.pop_front();
+                }
+                if (clf) tb_classifier_destroy(clf);
+                clf_bases = std::max<int64_t>(b.total() + b.total() / 4, batch_bases + (8 << 20));
+                clf_reads = std::max<int64_t>(b.n() + b.n() / 4, 1 << 16);
+                clf = tb_classifier_create(cfg.sets_a[(size_t)d], cfg.sets_b[(size_t)d], clf_bases, clf_reads, n_slots);
+                if (!clf) {
+                    set_rc(-7);
+                    set_err(tb_last_error());
+                }
+            }
+            if (clf && (int)inflight.size() == n_slots) {
+                complete(inflight.front());
+                inflight.pop_front();
+            }
+            if (clf && !b.ensure_results(b.n())) {
+                set_rc(-3);
+                set_err("pinned allocation for the results failed");
+            }
+            if (clf && rc.load() == 0) {
+                b.slot = next_slot;
+                next_slot = (next_slot + 1) % n_slots;
+                int src;
+                if (p->packed_ok)
+                    src = tb_classifier_submit_packed(clf, b.slot, &p->packed.pb, p->packed.offsets, b.ca, b.cb, b.sa,
+                                                      b.sb, b.bin);
+                else
+                    src = tb_classifier_submit(clf, b.slot, b.bases, b.offsets.data(), b.n(), b.ca, b.cb, b.sa, b.sb,
+                                               b.bin);
+                if (src != 0) {
+                    set_rc(-8);
+                    set_err(tb_last_error());
+                    p->failed = true;
+                    done_q.push(p);
+                } else {
+                    inflight.push_back(p);
+                }
+            } else {
+                p->failed = true;
+                done_q.push(p);
+            }
+        }
+        while (!inflight.empty()) {
+            complete(inflight.front());
+            inflight.pop_front();
+        }
+        if (clf) tb_classifier_destroy(clf);
+    };
+    std::vector<std::thread> workers;
+    for (int d = 0; d < n_dev; d++) workers.emplace_back(device_worker, d);
+
+    // ---- router ------------------------------------------------------------------------------
+    std::string tsv, rec_text;
+    double write_s = 0;
+    uint64_t n_a = 0, n_b = 0, n_u = 0, n_batches_done = 0;
+    auto emit = [&](PipeBatch *p) {
+        const auto t0 = Clock::now();
+        Batch *b = &p->b;
         tsv.clear();
-        for (int64_t i = 0; i < b->n() && rc == 0; i++) {
+        for (int64_t i = 0; i < b->n() && rc.load() == 0 && !p->failed; i++) {
             const Rec &r = b->recs[(size_t)i];
             const char *name = b->text.data() + r.name_off;
             const char *seq = b->bases + b->offsets[(size_t)i];
@@ -919,18 +1348,16 @@ int tb_classify_fastx(const char *reads_path, const hash_set *A, const hash_set 
                 rec_text.append(seq, seq_len);
                 rec_text += "\n+\n";
                 rec_text.append(b->text.data() + r.qual_off, r.qual_len);
-                rec_text += '\n';
             } else {
                 rec_text += '>';
                 rec_text.append(name, r.name_len);
                 rec_text += '\n';
                 rec_text.append(seq, seq_len);
-                rec_text += '\n';
             }
             const char bin = b->bin[i];
-            GzFileWriter &w = bin == 'A' ? wa : (bin == 'B' ? wb : wu);
+            BinWriter &w = bin == 'A' ? *wa : (bin == 'B' ? *wb : *wu);
             (bin == 'A' ? n_a : (bin == 'B' ? n_b : n_u))++;
-            w.append(rec_text.data(), rec_text.size());
+            w.record(rec_text.data(), rec_text.size());
             tsv.append(name, r.name_len);
             tsv += '\t';
             tsv += bin;
@@ -940,85 +1367,60 @@ int tb_classify_fastx(const char *reads_path, const hash_set *A, const hash_set 
             py_float_repr(b->sb[i], tsv);
             tsv += '\n';
         }
-        if (tsv_fd >= 0) {
+        if (cfg.tsv_fd >= 0) {
             size_t off = 0;
             while (off < tsv.size()) {
-                ssize_t w = ::write(tsv_fd, tsv.data() + off, tsv.size() - off);
-                if (w <= 0) { rc = -6; break; }
+                ssize_t w = ::write(cfg.tsv_fd, tsv.data() + off, tsv.size() - off);
+                if (w <= 0) { set_rc(-6); break; }
                 off += (size_t)w;
             }
         }
-        wa.drain(false);
-        wb.drain(false);
-        wu.drain(false);
+        wa->drain(false);
+        wb->drain(false);
+        wu->drain(false);
         write_s += seconds_since(t0);
         n_batches_done++;
-        free_q.push(b);
     };
-
-    bool done = false;
-    while (!done) {
-        Batch *b = full_q.pop();
-        done = b->last;
-        if (rc == 0 && b->n() > 0) {
-            if (!clf || b->total() > clf_bases || b->n() > clf_reads) {
-                // (re)create the classifier with room to spare; drain what is in flight first
-                while (!inflight.empty()) {
-                    finish_batch(inflight.front());
-                    inflight.pop_front();
-                }
-                if (clf) tb_classifier_destroy(clf);
-                clf_bases = std::max<int64_t>(b->total() + b->total() / 4, batch_bases + (8 << 20));
-                clf_reads = std::max<int64_t>(b->n() + b->n() / 4, 1 << 16);
-                clf = tb_classifier_create(A, B, clf_bases, clf_reads, n_slots);
-                if (!clf) {
-                    fprintf(stderr, "tb_classify_fastx: %s\n", tb_last_error());
-                    rc = -7;
-                }
-            }
-            if (rc == 0 && (int)inflight.size() == n_slots) {
-                finish_batch(inflight.front());
-                inflight.pop_front();
-            }
-            if (rc == 0) {
-                if (!b->ensure_results(b->n())) rc = -3;
-            }
-            if (rc == 0) {
-                b->slot = next_slot;
-                next_slot = (next_slot + 1) % n_slots;
-                if (tb_classifier_submit(clf, b->slot, b->bases, b->offsets.data(), b->n(), b->ca, b->cb,
-                                         b->sa, b->sb, b->bin) != 0) {
-                    fprintf(stderr, "tb_classify_fastx: %s\n", tb_last_error());
-                    rc = -8;
-                }
+    {
+        std::map<uint64_t, PipeBatch *> held;
+        uint64_t next_seq = 0;
+        bool finished = false;
+        while (!finished) {
+            PipeBatch *p = done_q.pop();
+            held[p->seq] = p;
+            for (auto it = held.find(next_seq); it != held.end(); it = held.find(next_seq)) {
+                PipeBatch *q = it->second;
+                held.erase(it);
+                emit(q);
+                finished = q->b.last;
+                next_seq++;
+                free_q.push(&q->b);
+                if (finished) break;
             }
         }
-        if (rc == 0 && b->n() > 0)
-            inflight.push_back(b);
-        else
-            free_q.push(b);
-    }
-    while (!inflight.empty()) {
-        if (rc == 0)
-            finish_batch(inflight.front());
-        else
-            free_q.push(inflight.front());
-        inflight.pop_front();
     }
     reader_thread.join();
+    packer.join();
+    for (auto &w : workers) w.join();
     const auto t_fin = Clock::now();
-    wa.finish();
-    wb.finish();
-    wu.finish();
+    // the reference's three locals are released in this order when main() returns
+    wa->finish();
+    wb->finish();
+    wu->finish();
     write_s += seconds_since(t_fin);
-    if (wa.failed || wb.failed || wu.failed) rc = rc ? rc : -9;
-    if (clf) tb_classifier_destroy(clf);
+    int out_rc = rc.load();
+    if (wa->failed || wb->failed || wu->failed) out_rc = out_rc ? out_rc : -9;
+    if (!err_text.empty()) {
+        fprintf(stderr, "tb_classify_fastx: %s\n", err_text.c_str());
+        tb_internal_set_error(err_text.c_str());
+    }
     if (!reader.error.empty()) {
         fprintf(stderr, "tb_classify_fastx: %s\n", reader.error.c_str());
-        if (!rc) tb_internal_set_error(reader.error.c_str());
-        rc = rc ? rc : -10;
+        if (!out_rc) tb_internal_set_error(reader.error.c_str());
+        out_rc = out_rc ? out_rc : -10;
     }
     if (stats) {
+        memset(stats, 0, sizeof *stats);
         stats->n_reads = reader.n_reads;
         stats->n_bases = reader.n_bases;
         stats->n_batches = n_batches_done;
@@ -1026,14 +1428,100 @@ int tb_classify_fastx(const char *reads_path, const hash_set *A, const hash_set 
         stats->reads_a = n_a;
         stats->reads_b = n_b;
         stats->reads_u = n_u;
-        stats->output_raw_bytes = wa.raw_bytes + wb.raw_bytes + wu.raw_bytes;
-        stats->output_gz_bytes = wa.gz_bytes + wb.gz_bytes + wu.gz_bytes;
+        stats->output_raw_bytes = wa->raw_bytes + wb->raw_bytes + wu->raw_bytes;
+        stats->output_gz_bytes = wa->out_bytes + wb->out_bytes + wu->out_bytes;
         stats->seconds_total = seconds_since(t_all);
         stats->seconds_parse = reader.seconds;
-        stats->seconds_gpu_wait = gpu_wait_s;
+        stats->seconds_gpu_wait = (double)gpu_wait_ns.load() * 1e-9;
         stats->seconds_write = write_s;
+        stats->seconds_inflate = reader.src.inflate_seconds();
+        stats->seconds_pack = pack_s;
+        stats->seconds_deflate_cpu = (double)deflate_ns.load() * 1e-9;
+        stats->devices_used = 0;
+        for (int u : used) stats->devices_used += (uint64_t)u;
     }
-    return rc;
+    return out_rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tb_classify_fastx_multi(const char *reads_path, const tb_stream_options *opt, const char *out_a,
+                            const char *out_b, const char *out_u, tb_stream_stats *stats)
+{
+    if (!reads_path || !opt || !out_a || !out_b || !out_u) return -1;
+    if (opt->n_devices < 1 || opt->n_devices > 64 || !opt->sets_a || !opt->sets_b) return -1;
+    PipelineConfig cfg;
+    cfg.reads_path = reads_path;
+    for (int d = 0; d < opt->n_devices; d++) {
+        if (!opt->sets_a[d] || !opt->sets_b[d]) return -1;
+        cfg.sets_a.push_back(opt->sets_a[d]);
+        cfg.sets_b.push_back(opt->sets_b[d]);
+    }
+    cfg.gzip_output = opt->gzip_output != 0;
+    cfg.gzip_level = (opt->gzip_level < 0 || opt->gzip_level > 9) ? 9 : opt->gzip_level;
+    cfg.fastq_encoder = opt->fastq_encoder != 0;
+    cfg.round_robin = opt->round_robin != 0;
+    cfg.py_text_mode = opt->py_text_mode;
+    cfg.py_buffer_size = opt->py_buffer_size;
+    cfg.tsv_fd = opt->tsv_fd;
+    cfg.batch_bases = opt->batch_bases;
+    cfg.threads = opt->n_threads;
+    cfg.out_a = out_a;
+    cfg.out_b = out_b;
+    cfg.out_u = out_u;
+    return run_pipeline(cfg, stats);
+}
+
+int tb_classify_fastx(const char *reads_path, const hash_set *A, const hash_set *B,
+                      const char *out_a, const char *out_b, const char *out_u, int gzip_level,
+                      int tsv_fd, int64_t batch_bases, int n_threads, tb_stream_stats *stats)
+{
+    if (!reads_path || !A || !B || !out_a || !out_b || !out_u) return -1;
+    // TB_FASTQ_GZIP=0 turns the FASTQ-aware encoder off (zlib at gzip_level for every chunk)
+    const char *fq_env = getenv("TB_FASTQ_GZIP");
+    tb_stream_options opt;
+    memset(&opt, 0, sizeof opt);
+    opt.n_devices = 1;
+    opt.sets_a = &A;
+    opt.sets_b = &B;
+    opt.gzip_output = 1;
+    opt.gzip_level = gzip_level;
+    opt.fastq_encoder = !(fq_env && strcmp(fq_env, "0") == 0);
+    opt.tsv_fd = tsv_fd;
+    opt.batch_bases = batch_bases;
+    opt.n_threads = n_threads;
+    return tb_classify_fastx_multi(reads_path, &opt, out_a, out_b, out_u, stats);
+}
+
+// testing aid (no GPU): the whole host pipeline -- reader, batches, router, the three writers
+// and the TSV -- with the classifier replaced by a pattern: record i goes to bins[i % n_bins]
+int tb_route_fastx(const char *reads_path, const char *bins, int64_t n_bins, int gzip_output, int gzip_level,
+                   int fastq_encoder, int n_workers, int round_robin, int py_text_mode, int64_t py_buffer_size,
+                   const char *out_a, const char *out_b, const char *out_u, int tsv_fd, int64_t batch_bases,
+                   int n_threads, tb_stream_stats *stats)
+{
+    if (!reads_path || !bins || n_bins < 1 || !out_a || !out_b || !out_u) return -1;
+    PipelineConfig cfg;
+    cfg.reads_path = reads_path;
+    cfg.stub_bins = bins;
+    cfg.n_stub = n_bins;
+    cfg.sets_a.assign((size_t)std::max(1, n_workers), nullptr);
+    cfg.sets_b = cfg.sets_a;
+    cfg.gzip_output = gzip_output != 0;
+    cfg.gzip_level = (gzip_level < 0 || gzip_level > 9) ? 9 : gzip_level;
+    cfg.fastq_encoder = fastq_encoder != 0;
+    cfg.round_robin = round_robin != 0;
+    cfg.py_text_mode = py_text_mode;
+    cfg.py_buffer_size = py_buffer_size;
+    cfg.tsv_fd = tsv_fd;
+    cfg.batch_bases = batch_bases;
+    cfg.threads = n_threads;
+    cfg.out_a = out_a;
+    cfg.out_b = out_b;
+    cfg.out_u = out_u;
+    return run_pipeline(cfg, stats);
 }
 
 // exposed for tests: Python's repr(float) as implemented above

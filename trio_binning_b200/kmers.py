@@ -174,7 +174,9 @@ class StreamStats(C.Structure):
 
     _fields_ = [(n, C.c_uint64) for n in ("n_reads", "n_bases", "n_batches", "input_bytes", "reads_a",
                                           "reads_b", "reads_u", "output_raw_bytes", "output_gz_bytes")] + \
-               [(n, C.c_double) for n in ("seconds_total", "seconds_parse", "seconds_gpu_wait", "seconds_write")]
+               [(n, C.c_double) for n in ("seconds_total", "seconds_parse", "seconds_gpu_wait", "seconds_write",
+                                          "seconds_inflate", "seconds_pack", "seconds_deflate_cpu")] + \
+               [("devices_used", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -182,6 +184,24 @@ class StreamStats(C.Structure):
 
 lib.tb_classify_fastx.argtypes = [C.c_char_p, HashSet, HashSet, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int,
                                   C.c_int, C.c_int64, C.c_int, C.POINTER(StreamStats)]
+
+
+class StreamOptions(C.Structure):
+    """`tb_stream_options` of include/trio_kmers_b200.h."""
+
+    _fields_ = [("n_devices", C.c_int), ("sets_a", C.POINTER(HashSet)), ("sets_b", C.POINTER(HashSet)),
+                ("gzip_output", C.c_int), ("gzip_level", C.c_int), ("fastq_encoder", C.c_int),
+                ("round_robin", C.c_int), ("tsv_fd", C.c_int), ("batch_bases", C.c_int64), ("n_threads", C.c_int),
+                ("py_text_mode", C.c_int), ("py_buffer_size", C.c_int64)]
+
+
+lib.tb_classify_fastx_multi.argtypes = [C.c_char_p, C.POINTER(StreamOptions), C.c_char_p, C.c_char_p, C.c_char_p,
+                                        C.POINTER(StreamStats)]
+lib.tb_set_clone.argtypes = [HashSet, C.c_int]
+lib.tb_set_clone.restype = HashSet
+lib.tb_route_fastx.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_int, C.c_int64, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int64, C.c_int,
+                               C.POINTER(StreamStats)]
 lib.tb_float_repr.argtypes = [C.c_double, C.c_char_p, C.c_int]
 lib.tb_fastx_dump.argtypes = [C.c_char_p, C.c_int]
 lib.tb_fastx_dump.restype = C.c_int64
@@ -590,17 +610,114 @@ class Classifier:
             pass
 
 
-def classify_fastx_file(reads_path: str, kmers_hap_a: "HashSet", kmers_hap_b: "HashSet", out_a: str,
-                        out_b: str, out_u: str, tsv_fd: int = -1, gzip_level: int = 9,
-                        batch_bases: int = 256 << 20, threads: int = 0) -> dict:
-    """Native streaming pipeline (tb_classify_fastx): parse, classify on the GPU, write the
-    three gzip outputs and the TSV.  Returns the pipeline's counters and stage timings."""
+def clone_kmer_hash_set(kmer_hash_set: "HashSet", device: int) -> "HashSet":
+    """Replica of a set on another GPU (device-to-device copy of the table)."""
+    handle = lib.tb_set_clone(kmer_hash_set, device)
+    if not handle:
+        raise RuntimeError(f"clone_kmer_hash_set: {_error()}")
+    return handle
+
+
+_PY_TEXT_IO = None
+
+
+def python_text_io_behaviour(directory: str = ".") -> Tuple[int, int]:
+    """How THIS interpreter's open(name, "w") buffers, for the native plain-text writer
+    (tb_stream_options.py_text_mode / py_buffer_size): the reference's --no-gzip-output files are
+    written through two such objects on one file (seq.py:127-130), so their flush points decide
+    the bytes.  Probed, not assumed: the rule changed between CPython releases."""
+    global _PY_TEXT_IO
+    import io
+    import tempfile
+
+    if _PY_TEXT_IO is None:
+        class _Log(io.BufferedIOBase):
+            def __init__(self):
+                self.sizes = []
+
+            def writable(self):
+                return True
+
+            def write(self, b):
+                self.sizes.append(len(b))
+                return len(b)
+
+        def calls(sizes):
+            log = _Log()
+            text = io.TextIOWrapper(log, encoding="utf-8")
+            for n in sizes:
+                text.write("x" * n)
+            text.flush()
+            return log.sizes
+
+        if calls([100, 9000]) == [9100]:
+            mode = 2                      # never flushes the pending list first
+        elif calls([5000, 5000]) == [5000, 5000]:
+            mode = 1                      # flushes when list + string would exceed the chunk
+        else:
+            mode = 0                      # flushes when the string alone is a chunk or more
+        assert calls([100, 9000]) == ([9100] if mode == 2 else [100, 9000])
+        _PY_TEXT_IO = mode
+    # BufferedWriter size (io.open derives it from the file system's block size, differently in
+    # different releases): fill a binary file in 512-byte steps; the first write that does not
+    # fit makes the buffer flush, and the file is then exactly one buffer long
+    buffer_size = 0
+    with tempfile.TemporaryDirectory(dir=directory) as tmp:
+        path = os.path.join(tmp, "probe")
+        with open(path, "wb") as f:
+            piece = b"x" * 512
+            for _ in range((16 << 20) // 512 + 2):
+                f.write(piece)
+                buffer_size = os.fstat(f.fileno()).st_size
+                if buffer_size:
+                    break
+    return _PY_TEXT_IO, buffer_size
+
+
+def classify_fastx_file(reads_path: str, kmers_hap_a, kmers_hap_b, out_a: str, out_b: str, out_u: str,
+                        tsv_fd: int = -1, gzip_level: int = 9, batch_bases: int = 256 << 20, threads: int = 0,
+                        gzip_output: bool = True, fastq_encoder: bool = True, round_robin: bool = False) -> dict:
+    """Native streaming pipeline (tb_classify_fastx_multi): parse, pack to 2 bits, classify on
+    the GPU(s), write the three outputs and the TSV, everything in input order.
+
+    kmers_hap_a / kmers_hap_b: one set each, or equally long lists of replicas, one per GPU to use
+    (`clone_kmer_hash_set`).  gzip_output=False is the reference's --no-gzip-output mode: plain
+    text, hapB's records written through a second handle on hapA's file (seq.py:127-130).
+    Returns the pipeline's counters and stage timings."""
+    sets_a = list(kmers_hap_a) if isinstance(kmers_hap_a, (list, tuple)) else [kmers_hap_a]
+    sets_b = list(kmers_hap_b) if isinstance(kmers_hap_b, (list, tuple)) else [kmers_hap_b]
+    if len(sets_a) != len(sets_b) or not sets_a:
+        raise ValueError("need one replica of each set per device")
+    opt = StreamOptions()
+    opt.n_devices = len(sets_a)
+    opt.sets_a = (HashSet * len(sets_a))(*sets_a)
+    opt.sets_b = (HashSet * len(sets_b))(*sets_b)
+    opt.gzip_output, opt.gzip_level, opt.fastq_encoder = int(gzip_output), gzip_level, int(fastq_encoder)
+    opt.round_robin, opt.tsv_fd, opt.batch_bases, opt.n_threads = int(round_robin), tsv_fd, batch_bases, threads
+    if not gzip_output:
+        opt.py_text_mode, opt.py_buffer_size = python_text_io_behaviour(os.path.dirname(os.path.abspath(out_a)))
     stats = StreamStats()
-    rc = lib.tb_classify_fastx(os.fsencode(reads_path), kmers_hap_a, kmers_hap_b, os.fsencode(out_a),
-                               os.fsencode(out_b), os.fsencode(out_u), gzip_level, tsv_fd, batch_bases,
-                               threads, C.byref(stats))
+    rc = lib.tb_classify_fastx_multi(os.fsencode(reads_path), C.byref(opt), os.fsencode(out_a), os.fsencode(out_b),
+                                     os.fsencode(out_u), C.byref(stats))
     if rc != 0:
         raise RuntimeError(f"tb_classify_fastx failed ({rc}): {_error()}")
+    return stats.as_dict()
+
+
+def route_fastx_file(reads_path: str, bins: str, out_a: str, out_b: str, out_u: str, tsv_fd: int = -1,
+                     gzip_output: bool = True, gzip_level: int = 6, fastq_encoder: bool = True, workers: int = 1,
+                     round_robin: bool = False, batch_bases: int = 1 << 20, threads: int = 4) -> dict:
+    """The host side of the native pipeline without a GPU (testing aid): record i is assigned
+    bins[i % len(bins)]; reader, batches, worker threads, in-order router, writers and TSV are
+    the product's."""
+    stats = StreamStats()
+    pattern = bins.encode("ascii")
+    mode, bufsize = (0, 0) if gzip_output else python_text_io_behaviour(os.path.dirname(os.path.abspath(out_a)))
+    rc = lib.tb_route_fastx(os.fsencode(reads_path), pattern, len(pattern), int(gzip_output), gzip_level,
+                            int(fastq_encoder), workers, int(round_robin), mode, bufsize, os.fsencode(out_a), os.fsencode(out_b),
+                            os.fsencode(out_u), tsv_fd, batch_bases, threads, C.byref(stats))
+    if rc != 0:
+        raise RuntimeError(f"tb_route_fastx failed ({rc}): {_error()}")
     return stats.as_dict()
 
 
