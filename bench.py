@@ -4,27 +4,27 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
 
-Workload (config.workload = "c2"): BASELINE.json configs[1] -- 10 000 synthetic long
-reads (gamma lengths, mean 20 kb, ~0.2 Gbases) against 10 M + 10 M distinct random
-21-mers, per GPU (weak scaling: every rank classifies its own 10 000 reads against
-its own replica of both sets; no collective on the data path).
+Workload (config.workload = "c3"): BASELINE.json configs[2] at its full SET sizes -- 150 M + 150 M
+distinct 21-mers (4.8 GB tagged table + 1 GB bitmap per GPU) -- and, per step and per GPU, a slice
+of its reads: 10 000 synthetic long reads (gamma lengths, mean 25 kb, ~0.25 Gbases).  Weak
+scaling: every rank classifies its own reads against its own replica of both sets; no collective
+on the data path.  configs[1], [3] and [4] (c2, c4, c5) are measured beside it at N = 1
+(`other_workloads`).
 
 A "step" is one pass of the hot path over that batch.
-  value  : bases/s with the batch already resident in HBM (pack + index + classify
-           + fix-up + decide kernels; CUDA events on the launching stream)
-  e2e    : bases/s through the C-ABI classifier with ASCII reads in PINNED HOST buffers --
-           H2D copies and the D2H copy of counts/scores/bins inside the timed region,
-           one slot (stream) per batch in flight.  Three routes are timed and the best
-           is reported (e2e.route; all three in e2e_variants): ASCII over the link and
-           packed on the device, packed to 2 bits by the host cores first, and a mix of
-           the two that keeps the PCIe link and the host cores busy together.
-  roofline: classify kernel only, SURVEY 8(d)'s algorithmic bytes (32 B per window of the merged
-           table + 0.25 B per base) over the kernel time against the measured HBM copy peak, with
-           three explanatory views beside it: the bytes the kernel really needs from HBM, its
-           sector-request rate against the measured L2 random-sector ceiling, and the busiest
-           unit per ncu.
-Inputs and tables exceed the 126 MB L2 (config.l2); value_l2_flushed is the same
-measurement with L2 overwritten between the timed steps.
+  value    bases/s with the batch already resident in HBM (pack + index + classify + fix-up +
+           decide kernels; CUDA events on the launching stream), steps back to back
+  value_sustained  the same over >= 2 s of back-to-back steps, clocks sampled
+  e2e      bases/s through the C ABI from HOST buffers in the form the product's parser emits
+           them -- pinned 2-bit-packed batches (tb_pack_reads) -- with the H2D copy of every
+           batch and the D2H copy of counts/scores/bins inside the timed region, two slots in
+           flight.  e2e_variants also times ASCII reads in pinned memory (packed on the device,
+           or packed by the host cores inside the timed region).
+  roofline the classify kernel against the resource that binds it on this workload: HBM for
+           c3/c4/c5 (every run of windows that share a minimizer costs one random bitmap fetch),
+           the integer ALU pipe for c2 (bitmap L2-resident).  See DESIGN.md section 4.
+  pipeline file -> files through the native pipeline (parse, pack, classify, compress, write),
+           measured here on a bounded synthetic FASTQ, stage times from tb_stream_stats.
 """
 import argparse
 import json
@@ -41,13 +41,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (n_reads, mean_len, k, n_a, n_b, fixed_len)
-    "c2": (10_000, 20_000, 21, 10_000_000, 10_000_000, False),
-    "c2_small": (1_000, 20_000, 21, 1_000_000, 1_000_000, False),   # quick local checks
-    "c5_slice": (1_000_000, 150, 21, 10_000_000, 10_000_000, True),  # short-read shape
+    # name: k, set sizes, reads per step and GPU, mean read length, fixed length?, one planted k-mer per N bases
+    "c3": dict(k=21, n_a=150_000_000, n_b=150_000_000, n_reads=10_000, mean_len=25_000, fixed=False, plant=1000,
+               baseline="configs[2]: 150M+150M 21-mers at full size; reads: a 10 000-read slice of the 1 M x 25 kb"),
+    "c2": dict(k=21, n_a=10_000_000, n_b=10_000_000, n_reads=10_000, mean_len=20_000, fixed=False, plant=1000,
+               baseline="configs[1]: 10 k long reads (mean 20 kb) vs 10M+10M 21-mers, complete"),
+    "c4": dict(k=31, n_a=400_000_000, n_b=400_000_000, n_reads=10_000, mean_len=25_000, fixed=False, plant=1000,
+               baseline="configs[3]: k=31, 400M+400M at full size; reads: a 10 000-read slice"),
+    "c5": dict(k=21, n_a=50_000_000, n_b=50_000_000, n_reads=2_000_000, mean_len=150, fixed=True, plant=100,
+               baseline="configs[4]: 50M+50M 21-mers at full size; reads: 2 M of the 100 M 150-bp reads"),
+    "c2_small": dict(k=21, n_a=1_000_000, n_b=1_000_000, n_reads=1_000, mean_len=20_000, fixed=False, plant=1000,
+                     baseline="quick local check"),
 }
 METRIC = "read_bases_classified_per_sec"
 UNIT = "bases/s"
+SM_COUNT, ALU_LANES_PER_SM = 148, 64  # B200: 4 sub-partitions x 16 INT32 lanes
 
 
 def dist_env():
@@ -101,9 +109,7 @@ class Dist:
 
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md), sampled
-    in-process through NVML every 10 ms (a looping `nvidia-smi -lms 20` child is the fallback;
-    `value_sampler_off` repeats the HBM-resident measurement after the sampler has stopped, as a
-    check that sampling does not disturb the kernels)."""
+    in-process through NVML every 10 ms (a looping `nvidia-smi -lms 20` child is the fallback)."""
 
     REASONS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
     Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -138,6 +144,7 @@ class ClockSampler:
             self._stop.wait(0.010)
 
     def start(self):
+        self.sm, self.smax, self.reasons = [], [], set()
         if self.mode == "nvml":
             try:
                 import pynvml as nv
@@ -163,6 +170,7 @@ class ClockSampler:
         if self.thread:
             self._stop.set()
             self.thread.join(timeout=2)
+            self.thread = None
             out["sampler"] = "nvml thread, 10 ms"
         elif self.proc:
             self.proc.terminate()
@@ -170,6 +178,7 @@ class ClockSampler:
                 self.proc.wait(timeout=5)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
+            self.proc = None
             self.f.close()
             out["sampler"] = "nvidia-smi -lms 20"
             for line in open(self.path):
@@ -197,9 +206,7 @@ class ClockSampler:
 
 def bind_to_gpu_numa_node(gpu_index):
     """Run this rank on the CPUs next to its GPU (NVML's ideal affinity) BEFORE any pinned
-    buffer is allocated, so that the staging memory is first-touched on the GPU's NUMA node:
-    with 8 ranks streaming 55 GB/s each, copies that cross the socket interconnect cap the
-    aggregate host-to-device rate."""
+    buffer is allocated, so that the staging memory is first-touched on the GPU's NUMA node."""
     try:
         import pynvml
 
@@ -226,22 +233,39 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def build_workload(name, rank, tmp_dir):
+def ncu_constants(workload):
+    """Per-launch counters of the classify kernel from the committed ncu captures
+    (profiles/ncu_kernels.json, written by tools/ncu_to_json.py from `ncu --set full` reports)."""
+    path = os.path.join(ROOT, "profiles", "ncu_kernels.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(workload)
+    return None
+
+
+def build_workload(name, rank):
     from trio_binning_b200 import synth
 
-    n_reads, mean_len, k, n_a, n_b, fixed = WORKLOADS[name]
-    keys_a, keys_b, path_a, path_b = synth.materialise_sets(tmp_dir, n_a, n_b, k, seed=42)
-    bases, offsets, _ = synth.random_reads(n_reads, mean_len, k, keys_a, keys_b, seed=43 + rank,
-                                           plant_every=1000, fixed_len=fixed)
-    return dict(k=k, keys_a=keys_a, keys_b=keys_b, path_a=path_a, path_b=path_b,
-                bases=bases, offsets=offsets, n_reads=n_reads, mean_len=mean_len, n_a=n_a, n_b=n_b)
+    w = WORKLOADS[name]
+    keys_a, keys_b = synth.sorted_disjoint_sets(w["n_a"], w["n_b"], w["k"], seed=1000 + w["k"])
+    bases, offsets, _ = synth.random_reads(w["n_reads"], w["mean_len"], w["k"], keys_a, keys_b, seed=43 + rank,
+                                           plant_every=w["plant"], fixed_len=w["fixed"])
+    return dict(w, name=name, keys_a=keys_a, keys_b=keys_b, bases=bases, offsets=offsets)
+
+
+def workload_config(args, wl, world):
+    return {"workload": f"{wl['name']}: {wl['n_a']}+{wl['n_b']} distinct {wl['k']}-mers (raw orientation, about half "
+                        f"findable; sorted-gap generator, seed {1000 + wl['k']}), {wl['n_reads']} reads per step and GPU, "
+                        f"mean {wl['mean_len']} bases, one planted k-mer per {wl['plant']} bases; {wl['baseline']}",
+            "reads_per_gpu": wl["n_reads"], "bases_per_gpu": int(wl["offsets"][-1]),
+            "k": wl["k"], "set_a": wl["n_a"], "set_b": wl["n_b"],
+            "l2": "every step reads a fresh 0.25-0.3 GB batch and probes tables (and, from c3 up, a bitmap) far larger "
+                  "than the 126 MB L2, so steps are timed back to back; value_l2_flushed repeats the measurement with "
+                  "a 512 MB buffer overwritten between steps",
+            "parallelism": f"reads sharded over {world} GPU(s), sets replicated, no collective"}
 
 
 # --------------------------------------------------------------------------- CPU arms
-def _ref_worker_init():
-    pass
-
-
 _REF = {}
 
 
@@ -259,28 +283,25 @@ def _ref_count_range(args):
 
 
 def cpu_reference_setup(wl):
-    """Load the reference's own CPU implementation (compiled from /root/reference/c/kmers.c
-    into oracle/_ref by oracle/build_oracle.py) and build both sets with it; fall back to
-    the oracle port if the compiled reference did not travel."""
+    """The reference's own CPU implementation (compiled unmodified from /root/reference/c/kmers.c
+    into oracle/_ref by oracle/build_oracle.py; the oracle port if that file did not travel) with
+    both sets at the workload's full size.  The sets' tables are filled by the oracle's insert
+    loop, which reproduces the reference's layout slot for slot (tests/test_oracle.py) without
+    writing and re-parsing 6.6 GB of text: set construction is not what is timed."""
+    from concurrent.futures import ThreadPoolExecutor
+
     from oracle.oracle import CompiledReference, Oracle
 
+    orc = Oracle()
+    with ThreadPoolExecutor(2) as pool:  # ctypes drops the GIL: both tables fill side by side
+        fa = pool.submit(orc.set_from_ints, wl["keys_a"], wl["k"])
+        fb = pool.submit(orc.set_from_ints, wl["keys_b"], wl["k"])
+        A, B = fa.result(), fb.result()
     if CompiledReference.available():
-        lib = CompiledReference()
-        devnull = os.open(os.devnull, os.O_WRONLY)
-        saved = os.dup(2)
-        os.dup2(devnull, 2)  # the reference prints progress to stderr
-        try:
-            A, B = lib.set_from_file(wl["path_a"]), lib.set_from_file(wl["path_b"])
-        finally:
-            os.dup2(saved, 2)
-            os.close(devnull)
-            os.close(saved)
-        kind = "reference"
+        lib, kind = CompiledReference(), "reference"
     else:
-        lib = Oracle()
-        A, B = lib.set_from_ints(wl["keys_a"], wl["k"]), lib.set_from_ints(wl["keys_b"], wl["k"])
-        kind = "port"
-    _REF.update(lib=lib, A=A, B=B, bases=wl["bases"], offsets=wl["offsets"])
+        lib, kind = orc, "port"
+    _REF.update(lib=lib, A=A, B=B, bases=wl["bases"], offsets=wl["offsets"], orc=orc)
     return kind
 
 
@@ -303,13 +324,13 @@ def cpu_time_reads(read_lo, read_hi, procs):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return 0
-    tmp_dir = os.path.join(tempfile.gettempdir(), "tb_bench_data")
-    wl = build_workload(args.workload, 0, tmp_dir)
+    wl = build_workload(args.workload, 0)
+    t0 = time.perf_counter()
     kind = cpu_reference_setup(wl)
+    setup_s = time.perf_counter() - t0
     procs = os.cpu_count() or 1
     # bounded sample per step: ~2.5 s of work at ~0.8 Mbases/s/core
-    mean_len = wl["mean_len"]
-    reads_per_step = max(procs, int(2.5 * 0.8e6 * procs / mean_len))
+    reads_per_step = max(procs, int(2.5 * 0.8e6 * procs / wl["mean_len"]))
     reads_per_step = min(reads_per_step, wl["n_reads"])
     times, bases_done = [], []
     cursor = 0
@@ -326,10 +347,11 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic", "config": workload_config(args, wl),
+        "data": "synthetic", "config": workload_config(args, wl, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind,
                          "sample": f"{reads_per_step} reads (~{total_b // args.steps} bases) per step, "
-                                   f"{procs} forked processes over reads, sets built once (untimed)"},
+                                   f"{procs} forked processes over reads, both full-size sets built once "
+                                   f"(untimed, {setup_s:.0f} s)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -337,19 +359,171 @@ def run_reference_arm(args, rank, world):
     return 0
 
 
-def workload_config(args, wl):
-    return {"workload": f"{args.workload}: {wl['n_reads']} reads, mean {wl['mean_len']} bases, "
-                        f"k={wl['k']}, {wl['n_a']}+{wl['n_b']} distinct random {wl['k']}-mers "
-                        f"(raw orientation, ~50% findable), per GPU",
-            "reads_per_gpu": wl["n_reads"], "bases_per_gpu": int(wl["offsets"][-1]),
-            "k": wl["k"], "set_a": wl["n_a"], "set_b": wl["n_b"],
-            "l2": "per step the kernels read 250 MB of fresh input (ASCII + packed) and probe 2 x 160 MB of "
-                  "tables at random, both larger than the 126 MB L2, so steps are timed back to back; "
-                  "value_l2_flushed repeats the measurement with a 512 MB buffer overwritten between steps",
-            "parallelism": f"reads sharded over {args.gpus} GPU(s), sets replicated, no collective"}
-
-
 # --------------------------------------------------------------------------- GPU arm
+def classify_rooflines(wl, fi, windows, passes, runs, total, cls_ms, clocks, gather):
+    """The classify kernel against the two resources that can bind it.  Algorithmic work per launch
+    (restating SURVEY 8(d) for the merged, pre-filtered lookup):
+      HBM:  32 B per bitmap sector fetch (one per run of consecutive windows of a lane that share a
+            minimizer: `runs`, counted on the device) + 32 B per window that passes the bitmap (one
+            bucket of the tagged A+B table) + 0.25 B per base of the 2-bit read stream
+      ALU:  integer-pipe thread instructions per window, counted by ncu on this workload
+            (sm__inst_executed_pipe_alu x 32 / windows; profiles/ncu_kernels.json)"""
+    hbm_gbs, peak_src = measured_peaks()
+    cls_s = cls_ms * 1e-3
+    ncu = ncu_constants(wl["name"]) or {}
+    algo_bytes = 32.0 * runs + 32.0 * passes + 0.25 * total
+    hbm = {"bound": "hbm", "achieved": algo_bytes / cls_s / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+           "frac": algo_bytes / cls_s / 1e9 / hbm_gbs, "peak_source": peak_src,
+           "algorithmic_bytes_per_launch": algo_bytes,
+           "algorithmic_bytes_definition": "32 B x bitmap sector fetches (runs of windows sharing a minimizer, "
+                                           "counted on the device) + 32 B x windows passing the bitmap + 0.25 B x bases",
+           "bitmap_sector_fetches_per_launch": runs, "fetches_per_window": runs / max(1, windows),
+           "traffic": ncu.get("dram_bytes_per_launch"), "traffic_source": ncu.get("source"),
+           "random_fetches_per_s": (runs + passes) / cls_s,
+           "random_sector_ceiling_per_s": gather.get("dram"),
+           "frac_of_random_sector_ceiling": ((runs + passes) / cls_s / gather["dram"]) if gather.get("dram") else None}
+    if ncu.get("dram_bytes_per_launch"):
+        # the captured launch's own traffic over ITS duration: how busy HBM really is
+        hbm["traffic_gbs_at_capture"] = ncu["dram_bytes_per_launch"] / (ncu["duration_ms"] * 1e-3) / 1e9
+        hbm["traffic_frac_of_peak_at_capture"] = hbm["traffic_gbs_at_capture"] / hbm_gbs
+        hbm["traffic_over_algorithmic"] = ncu["dram_bytes_per_launch"] / algo_bytes
+    alu = None
+    if ncu.get("alu_thread_insts_per_window") and clocks.get("sm_mhz"):
+        ops = ncu["alu_thread_insts_per_window"] * windows
+        peak = SM_COUNT * ALU_LANES_PER_SM * clocks["sm_mhz"] * 1e6
+        alu = {"bound": "int-alu", "achieved": ops / cls_s / 1e12, "peak": peak / 1e12, "unit": "Tinst/s",
+               "frac": ops / cls_s / peak,
+               "alu_thread_insts_per_window": ncu["alu_thread_insts_per_window"],
+               "peak_definition": f"{SM_COUNT} SMs x {ALU_LANES_PER_SM} integer lanes x {clocks['sm_mhz']:.0f} MHz "
+                                  "(median SM clock sampled during this run)",
+               "source": ncu.get("source"), "alu_pipe_pct_at_capture": ncu.get("alu_pipe_pct")}
+    # the binding resource: whichever is closer to its peak
+    main = hbm
+    if alu and alu["frac"] > (hbm.get("traffic_frac_of_peak_at_capture") or hbm["frac"]):
+        main = alu
+    out = dict(main)
+    out["kernel"] = f"k_classify_pair_mini<{wl['k']},8,{fi['bits_per_key']},2>" if fi.get("minimizer") else "k_classify*"
+    out["kernel_ms"] = cls_ms
+    out["windows_per_launch"] = windows
+    out["bitmap_log2_bits"] = fi["log2_bits"]
+    out["bitmap_pass_fraction"] = passes / max(1, windows)
+    out["views"] = {"hbm": hbm, "int_alu": alu}
+    return out
+
+
+def measure_resident(clf, kmers, wl, steps, warmup, want_flush=True):
+    """HBM-resident figures of one workload on an existing classifier whose slot 0 holds the batch."""
+    clf.rerun_resident(0, max(3, warmup))
+    res_ms, cls_ms = clf.rerun_resident(0, steps)
+    out = {"res_ms": res_ms, "cls_ms": cls_ms}
+    if want_flush:
+        out["flush_ms"], _ = clf.rerun_resident(0, steps, flush_bytes=512 << 20)
+    return out
+
+
+def run_other_workload(name, kmers, synth, args, gather):
+    """c2 / c4 / c5 beside the headline (N = 1 only): kernel-only and HBM-resident step rates."""
+    wl = build_workload(name, 0)
+    k = wl["k"]
+    A = kmers.create_kmer_hash_set_from_ints(wl["keys_a"], k)
+    B = kmers.create_kmer_hash_set_from_ints(wl["keys_b"], k)
+    total, n_reads = int(wl["offsets"][-1]), wl["n_reads"]
+    windows = synth.total_windows(wl["offsets"], k)
+    clf = kmers.Classifier(A, B, max_bases=total, max_reads=n_reads, n_slots=2)
+    clf.submit(0, wl["bases"], wl["offsets"])
+    ca, cb, *_ = (x.copy() for x in clf.result(0))
+    pb = kmers.PackedBatch(total, n_reads)
+    pb.pack(wl["bases"], wl["offsets"], k)
+
+    def packed_pass(n_steps):
+        clf.mark(0, 0)
+        for i in range(n_steps):
+            slot = i & 1
+            if i >= 2:
+                clf.wait(slot)
+            clf.submit_packed(slot, pb)
+        clf.mark(0, 1)
+        clf.mark(1, 1)
+        clf.wait(0)
+        clf.wait(1)
+        return max(clf.elapsed_ms(0, 0, 0, 1), clf.elapsed_ms(0, 0, 1, 1))
+
+    packed_pass(3)
+    pa, pbb, *_ = clf.result(0)
+    assert (pa == ca).all() and (pbb == cb).all(), "host-packed path differs from the ASCII path"
+    steps = max(5, args.steps // 2)
+    e2e_ms = packed_pass(steps)
+    clf.submit(0, wl["bases"], wl["offsets"])
+    clf.wait(0)
+    sampler = ClockSampler(0)
+    sampler.start()
+    m = measure_resident(clf, kmers, wl, steps, args.warmup, want_flush=False)
+    clocks = sampler.stop()
+    fi, passes, runs = clf.filter_info(), clf.filter_passes(0), clf.sector_runs(0)
+    roof = classify_rooflines(wl, fi, windows, passes, runs, total, m["cls_ms"] / steps, clocks, gather)
+    out = {"workload": wl["baseline"], "k": k, "set_a": wl["n_a"], "set_b": wl["n_b"], "reads": n_reads, "bases": total,
+           "value": total / (m["res_ms"] / steps * 1e-3), "unit": UNIT, "ms_per_step": m["res_ms"] / steps,
+           "kernel_only": total / (m["cls_ms"] / steps * 1e-3),
+           "e2e": {"value": total / (e2e_ms / steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": pb.h2d_bytes,
+                   "d2h_bytes_per_step": n_reads * 25, "route": "packed"},
+           "roofline": roof, "clocks": clocks, "steps": steps,
+           "hits": [int(ca.sum()), int(cb.sum())]}
+    clf.close()
+    kmers.destroy_kmer_hash_set(A)
+    kmers.destroy_kmer_hash_set(B)
+    return out
+
+
+def run_pipeline_leg(kmers, synth, A, B, k, keys_a, keys_b, gbases):
+    """file -> files through the native pipeline on a bounded synthetic FASTQ (HiFi-like: 15 kb
+    reads, run-length qualities), one GPU: plain, gzip and BGZF input; FASTQ-aware encoder and
+    zlib -6 output; plain-text output.  Times are the pipeline's own (tb_stream_stats): start-up
+    (interpreter, CUDA context, set build) is not in them."""
+    tmp = tempfile.mkdtemp(prefix="tb_pipe_")
+    n_reads = max(100, int(gbases * 1e9 / 15_000))
+    t0 = time.perf_counter()
+    bases, offsets, _ = synth.random_reads(n_reads, 15_000, k, keys_a, keys_b, seed=99, plant_every=1000)
+    rng = np.random.default_rng(5)
+    plain = os.path.join(tmp, "reads.fastq")
+    with open(plain, "wb") as f:
+        qual_pool = np.repeat(rng.integers(40, 94, size=1 << 16, dtype=np.uint8), rng.integers(1, 60, size=1 << 16))
+        for r in range(n_reads):
+            s = bases[offsets[r]:offsets[r + 1]]
+            start = int(rng.integers(0, len(qual_pool) - len(s) - 1))
+            f.write(b"@m64_%d/ccs np=12\n" % r + s.tobytes() + b"\n+\n" + qual_pool[start:start + len(s)].tobytes() + b"\n")
+    size = os.path.getsize(plain)
+    gz = os.path.join(tmp, "reads_gz.fastq.gz")
+    bgzf = os.path.join(tmp, "reads_bgzf.fastq.gz")
+    kmers.gzip_copy(plain, gz, level=6, threads=os.cpu_count() or 4, piece=1 << 20)
+    kmers.gzip_copy(plain, bgzf, level=6, threads=os.cpu_count() or 4, piece=1 << 20, bgzf=True)
+    gen_s = time.perf_counter() - t0
+    total = int(offsets[-1])
+    runs = []
+    for tag, path, kw in (("plain in, gzip out (FASTQ-aware encoder)", plain, {}),
+                          ("gzip -6 in, gzip out (FASTQ-aware encoder)", gz, {}),
+                          ("BGZF in, gzip out (FASTQ-aware encoder)", bgzf, {}),
+                          ("plain in, gzip out (zlib -6)", plain, dict(fastq_encoder=False, gzip_level=6)),
+                          ("plain in, plain out (--no-gzip-output)", plain, dict(gzip_output=False))):
+        d = tempfile.mkdtemp(dir=tmp)
+        with open(os.path.join(d, "tsv"), "wb") as t:
+            st = kmers.classify_fastx_file(path, A, B, os.path.join(d, "A"), os.path.join(d, "B"), os.path.join(d, "U"),
+                                           tsv_fd=t.fileno(), batch_bases=64 << 20, **kw)
+        runs.append({"run": tag, "wall_s": st["seconds_total"], "mbases_per_s": total / st["seconds_total"] / 1e6,
+                     "input_mb_per_s": os.path.getsize(path) / st["seconds_total"] / 1e6,
+                     "seconds": {key[8:]: round(st[key], 3) for key in st if key.startswith("seconds_") and key != "seconds_total"},
+                     "output_bytes": st["output_gz_bytes"], "output_raw_bytes": st["output_raw_bytes"],
+                     "reads_abu": [st["reads_a"], st["reads_b"], st["reads_u"]]})
+        for name in os.listdir(d):
+            os.unlink(os.path.join(d, name))
+    for p_ in (plain, gz, bgzf):
+        os.unlink(p_)
+    return {"what": "native pipeline, file -> three files + TSV, one GPU, inside one process (start-up and set build "
+                    "excluded); seconds.parse is the reader thread's wall time, inflate / deflate_cpu are summed over "
+                    "their threads, gpu_wait over the device workers",
+            "reads": n_reads, "bases": total, "fastq_bytes": size, "gzip_input": "4 MiB members, zlib -6 (decoded serially, like one member)", "host_threads": os.cpu_count(),
+            "generate_s": round(gen_s, 1), "runs": runs}
+
+
 def run_gpu_arm(args, rank, local_rank, world):
     from trio_binning_b200 import kmers, synth
 
@@ -358,28 +532,34 @@ def run_gpu_arm(args, rank, local_rank, world):
     numa = bind_to_gpu_numa_node(local_rank)
     dist = Dist(world, "nccl")
     kmers.set_device(local_rank)
-    tmp_dir = os.path.join(tempfile.gettempdir(), f"tb_bench_data_r{rank}" if world > 1 else "tb_bench_data")
     t_setup = time.perf_counter()
-    wl = build_workload(args.workload, rank, tmp_dir)
+    wl = build_workload(args.workload, rank)
     k = wl["k"]
-    A = kmers.create_kmer_hash_set(wl["path_a"])
-    B = kmers.create_kmer_hash_set(wl["path_b"])
+    A = kmers.create_kmer_hash_set_from_ints(wl["keys_a"], k)
+    B = kmers.create_kmer_hash_set_from_ints(wl["keys_b"], k)
     build_ms = A.contents.build_ms + B.contents.build_ms
     bases, offsets = wl["bases"], wl["offsets"]
     total = int(offsets[-1])
     n_reads = wl["n_reads"]
     windows = synth.total_windows(offsets, k)
 
-    n_slots = 5  # two for the double-buffered routes, up to five for the hybrid cycle below
+    n_slots = 2
     clf = kmers.Classifier(A, B, max_bases=total, max_reads=n_reads, n_slots=n_slots)
-    for slot in range(2):  # fill the pinned staging buffers once: these ARE the host inputs
+    for slot in range(2):  # fill the pinned staging buffers once: these ARE the host inputs of the ASCII routes
         hb, ho = clf.staging(slot)
         hb[:total] = bases
         ho[: n_reads + 1] = offsets
+    host_threads = max(1, (len(os.sched_getaffinity(0)) or 1) // world)  # ranks share the host cores
+    pbs = [kmers.PackedBatch(total, n_reads) for _ in range(n_slots)]
+    for pb in pbs:
+        pb.pack(bases, offsets, k, threads=host_threads)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        pbs[0].pack(bases, offsets, k, threads=host_threads)
+    pack_s = (time.perf_counter() - t0) / 5
     setup_s = time.perf_counter() - t_setup
 
-    # ---- end to end: pinned host -> H2D -> kernels -> D2H, two slots in flight
-    def e2e_pass(n_steps):
+    def ascii_pass(n_steps):
         clf.mark(0, 0)
         for i in range(n_steps):
             slot = i & 1
@@ -391,31 +571,6 @@ def run_gpu_arm(args, rank, local_rank, world):
         clf.wait(0)
         clf.wait(1)
         return max(clf.elapsed_ms(0, 0, 0, 1), clf.elapsed_ms(0, 0, 1, 1))
-
-    e2e_pass(max(3, args.warmup))
-    ca, cb, sa, sb, bins = (x.copy() for x in clf.result(0))
-    hits_a = int(ca.sum())
-    probes = 2 * windows - hits_a
-
-    sampler = ClockSampler(local_rank)
-    dist.barrier()
-    sampler.start()
-    e2e_ms = e2e_pass(args.steps)
-    dist.barrier()
-    e2e_ms = dist.reduce(e2e_ms, "MAX")
-
-    # ---- same batch through the host-packed entry (north_star's "pinned, 2-bit-packed
-    # ---- batches"): (a) packing timed on its own, (b) packed batches already in pinned
-    # ---- memory -> H2D of 0.25 B/base -> kernels -> D2H, (c) ASCII in, host pack INSIDE
-    # ---- the timed region, then (b)
-    host_threads = max(1, (len(os.sched_getaffinity(0)) or 1) // world)  # ranks share the host cores
-    pbs = [kmers.PackedBatch(total, n_reads) for _ in range(n_slots)]
-    for pb in pbs:
-        pb.pack(bases, offsets, k, threads=host_threads)
-    t0 = time.perf_counter()
-    for _ in range(10):
-        pbs[0].pack(bases, offsets, k, threads=host_threads)
-    pack_s = (time.perf_counter() - t0) / 10
 
     def packed_pass(n_steps, pack_inside):
         clf.mark(0, 0)
@@ -432,63 +587,48 @@ def run_gpu_arm(args, rank, local_rank, world):
         clf.wait(1)
         return max(clf.elapsed_ms(0, 0, 0, 1), clf.elapsed_ms(0, 0, 1, 1))
 
-    def hybrid_pass(n_cycles, n_packed):
-        """ASCII in all cases.  One cycle = one batch on the ASCII route (slot 0: the PCIe link does
-        the work, the device packs) followed by `n_packed` batches on the host-pack route (slots
-        1..n_packed: host cores pack, 0.25 B/base cross the link) -- the two resources work in
-        parallel, every batch in its own slot.  Returns ms for n_cycles * (1 + n_packed) batches."""
-        cyc = 1 + n_packed
-        clf.mark(0, 0)
-        for i in range(n_cycles * cyc):
-            slot = i % cyc
-            if i >= cyc:
-                clf.wait(slot)
-            if slot == 0:
-                clf.submit(0, None, None, n_reads=n_reads)
-            else:
-                pbs[slot].pack(bases, offsets, k, threads=host_threads)
-                clf.submit_packed(slot, pbs[slot])
-        for s_ in range(cyc):
-            clf.mark(s_, 1)
-        for s_ in range(cyc):
-            clf.wait(s_)
-        return max(clf.elapsed_ms(0, 0, s_, 1) for s_ in range(cyc))
-
-    packed_pass(3, False)
+    warm = max(3, args.warmup)
+    ascii_pass(warm)
+    ca, cb, sa, sb, bins = (x.copy() for x in clf.result(0))
+    hits_a = int(ca.sum())
+    probes = 2 * windows - hits_a
+    packed_pass(warm, False)
     pca, pcb, *_ = clf.result(0)
     assert (pca == ca).all() and (pcb == cb).all(), "host-packed path differs from the ASCII path"
+
+    sampler = ClockSampler(local_rank)
+    # ---- end to end, the product's route: pinned 2-bit batches -> H2D -> kernels -> D2H
     dist.barrier()
+    sampler.start()
     e2e_packed_ms = dist.reduce(packed_pass(args.steps, False), "MAX")
     dist.barrier()
-    e2e_hostpack_ms = dist.reduce(packed_pass(max(3, args.steps // 5), True), "MAX") * args.steps / max(3, args.steps // 5)
-    # the mix of the two routes that balances link and host cores depends on the box: time
-    # 1 ASCII : 1..4 host-packed and keep the best (all are the same public calls)
-    hybrid = {}
-    for n_packed in range(1, n_slots):
-        cyc = 1 + n_packed
-        hybrid_pass(2, n_packed)
-        dist.barrier()
-        n_cycles = max(3, args.steps // (2 * cyc))
-        ms = dist.reduce(hybrid_pass(n_cycles, n_packed), "MAX")
-        hybrid[n_packed] = ms / (n_cycles * cyc)  # ms per batch
-    hyb_n = min(hybrid, key=hybrid.get)
-    e2e_hybrid_ms = hybrid[hyb_n] * args.steps
+    clocks_e2e = sampler.stop()
+    # ---- the same from ASCII in pinned memory: packed on the device, or by the host cores in the timed region
+    e2e_ascii_ms = dist.reduce(ascii_pass(args.steps), "MAX")
+    dist.barrier()
+    few = max(3, args.steps // 5)
+    e2e_hostpack_ms = dist.reduce(packed_pass(few, True), "MAX") * args.steps / few
     # leave an ASCII batch resident in slot 0 for the device-only timing below
     clf.submit(0, None, None, n_reads=n_reads)
     clf.wait(0)
 
     # ---- HBM-resident: device part only, CUDA events on the slot's stream
-    clf.rerun_resident(0, max(3, args.warmup))
+    clf.rerun_resident(0, warm)
     dist.barrier()
+    sampler.start()
     res_ms, cls_ms = clf.rerun_resident(0, args.steps)
     dist.barrier()
     clocks = sampler.stop()
-    quiet_ms, _ = clf.rerun_resident(0, args.steps)  # same measurement with the clock sampler off
-    quiet_ms_max = dist.reduce(quiet_ms, "MAX")
-    # same, with a 512 MB buffer overwritten between the timed steps (cold L2 every step)
-    flush_ms, flush_cls_ms = clf.rerun_resident(0, args.steps, flush_bytes=512 << 20)
+    flush_ms, _ = clf.rerun_resident(0, args.steps, flush_bytes=512 << 20)
+    # ---- sustained: >= 2 s of back-to-back steps (the burst above lasts milliseconds)
+    per_step = res_ms / args.steps
+    sus_iters = int(min(4096, max(args.steps, 2200.0 / per_step)))
+    sampler.start()
+    sus_ms, sus_cls_ms = clf.rerun_resident(0, sus_iters)
+    clocks_sus = sampler.stop()
     res_ms_max = dist.reduce(res_ms, "MAX")
     flush_ms_max = dist.reduce(flush_ms, "MAX")
+    sus_ms_max = dist.reduce(sus_ms, "MAX")
     total_all = dist.reduce(total, "SUM")
     probes_all = dist.reduce(probes, "SUM")
 
@@ -498,168 +638,106 @@ def run_gpu_arm(args, rank, local_rank, world):
     assert (ca2 == ca).all() and (cb2 == cb).all(), "re-run changed the results"
     finfo = clf.filter_info()
     passes = clf.filter_passes(0)
+    runs = clf.sector_runs(0)
 
     line = None
     if rank == 0:
-        hbm_gbs, peak_src = measured_peaks()
-        cls_ms_per = cls_ms / args.steps
-        cls_s = cls_ms_per * 1e-3
-        ceil_dram = ceil_l2 = None
+        gather = {}
         if not args.no_gather:
             # random-32-B-sector request ceilings of THIS GPU, same run: a table far larger
             # than L2 (HBM random-access bound) and one that stays L2-resident
-            ceil_dram = max(kmers.gather_bench(4 << 30, mlp, tpb, bps, 48, 0)[0]
-                            for mlp, tpb, bps in ((8, 256, 8), (16, 256, 4), (4, 512, 4)))
-            ceil_l2 = max(kmers.gather_bench(32 << 20, mlp, tpb, bps, 256, 0)[0]
-                          for mlp, tpb, bps in ((8, 256, 8), (16, 256, 4), (8, 128, 16)))
-        if finfo["log2_bits"]:
-            # filtered kernels: one L2 sector request per window (bitmap) + one (pair table) or
-            # two (A and B) HBM sector requests per window that passed the bitmap
-            pair = finfo["pair_buckets"] > 0
-            table_probes = passes if pair else 2 * passes
-            sector_requests = windows + table_probes
-            # 32 B per probe + 0.25 B per base; with the merged A+B table one lookup per
-            # window answers both sets, so 32 B per WINDOW (no phantom second probes)
-            model_units = windows if pair else probes
-            algo_bytes = 32.0 * model_units + 0.25 * total
-            achieved = algo_bytes / cls_s / 1e9
-            l2_bytes = 32.0 * sector_requests + 0.25 * total
-            hbm_actual_bytes = 32.0 * table_probes + 0.25 * total + (1 << finfo["log2_bits"]) / 8
-            roofline = {
-                "bound": "hbm",
-                "kernel": (f"k_classify_pair_mini<{k},8,{finfo['bits_per_key']}>" if finfo.get("minimizer") else
-                           f"k_classify_pair<{k},16,{finfo['bits_per_key']}>") if pair else f"k_classify_filtered<{k},16>",
-                "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                "peak_source": peak_src,
-                "traffic": None,
-                "algorithmic_bytes_per_launch": algo_bytes,
-                "algorithmic_bytes_definition": "SURVEY 8(d): 32 B x %s + 0.25 B x bases" % (
-                    "windows (merged A+B table: one lookup per window)" if pair else "probes"),
-                "note": "frac > 1 means the kernel no longer moves the bytes the 8(d) model charges: the bitmap "
-                        "pre-filter (2^%d bits, %d bit(s) per key, %s, read evict_last) answers %.2f%% of the "
-                        "windows from L1/L2, and only the survivors read %s from HBM. What the kernel does fetch "
-                        "from HBM is in hbm_actual{} (and, measured, in traffic); its cache-side request rate "
-                        "against the measured L2 random-sector ceiling is in l2_requests{}"
-                        % (finfo["log2_bits"], finfo["bits_per_key"],
-                           "sectors addressed by the k-mers' minimizers so that consecutive windows re-use them from L1"
-                           if finfo.get("minimizer") else "L2-resident",
-                           100.0 * (1 - passes / max(1, windows)),
-                           "one bucket of the tagged A+B pair table" if pair else "one bucket of A and one of B"),
-                "windows_per_launch": windows, "filter_passes_per_launch": passes,
-                "kernel_ms": cls_ms_per, "kernel_share_of_step": cls_ms / res_ms,
-                "reference_probes_per_launch": probes, "reference_probes_per_s": probes / cls_s,
-                "hbm_actual": {
-                    "what": "bytes this kernel must fetch from HBM per launch: 32 B per bitmap survivor, the "
-                            "2-bit read stream, the bitmap once",
-                    "bytes_per_launch": hbm_actual_bytes,
-                    "achieved": hbm_actual_bytes / cls_s / 1e9, "peak": hbm_gbs, "unit": "GB/s",
-                    "frac": hbm_actual_bytes / cls_s / 1e9 / hbm_gbs,
-                    "table_probes_per_s": table_probes / cls_s,
-                    "random_sector_ceiling_per_s": ceil_dram,
-                    "frac_of_random_sector_ceiling": (table_probes / cls_s / ceil_dram) if ceil_dram else None},
-                "l2_requests": {
-                    "what": "one 32-B bitmap sector request per window + one per table probe, against the "
-                            "random-32-B-sector request ceiling of an L2-resident table measured in this run "
-                            "(tb_gather_bench, 32 MB table, requests that bypass L1)",
-                    "sector_requests_per_launch": sector_requests,
-                    "achieved": l2_bytes / cls_s / 1e9,
-                    "peak": (ceil_l2 * 32 / 1e9) if ceil_l2 else None, "unit": "GB/s",
-                    "frac": (l2_bytes / cls_s / 1e9 / (ceil_l2 * 32 / 1e9)) if ceil_l2 else None},
-            }
-        else:
-            algo_bytes = 32.0 * probes + 0.25 * total
-            achieved = algo_bytes / cls_s / 1e9
-            roofline = {"bound": "hbm", "kernel": f"k_classify<{k},4>", "achieved": achieved, "peak": hbm_gbs,
-                        "unit": "GB/s", "frac": achieved / hbm_gbs, "peak_source": peak_src, "traffic": None,
-                        "algorithmic_bytes_per_launch": algo_bytes, "probes_per_launch": probes,
-                        "kernel_ms": cls_ms_per, "probes_per_s": probes / cls_s,
-                        "kernel_share_of_step": cls_ms / res_ms,
-                        "random_sector_ceiling_per_s": ceil_dram,
-                        "frac_of_random_sector_ceiling": (probes / cls_s / ceil_dram) if ceil_dram else None}
-        traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(traffic_file):
-            with open(traffic_file) as f:
-                t = json.load(f).get(roofline["kernel"].split("<")[0])
-            if t:
-                roofline["traffic"] = t["dram_bytes_per_launch"]
-                roofline["traffic_source"] = t["source"]
-                if "alu_pipe_pct" in t:
-                    roofline["binding_resource"] = {
-                        "unit": "integer ALU pipe", "pct_of_peak": t["alu_pipe_pct"],
-                        "l1_sector_hit_pct": t["l1_sector_hit_pct"], "source": "ncu (traffic_source)",
-                        "what": "the busiest unit per ncu; the minimizer-addressed sectors let L1 serve most "
-                                "bitmap requests, which is why l2_requests.frac can exceed 1 as well"}
+            gather["dram"] = max(kmers.gather_bench(4 << 30, mlp, tpb, bps, 48, 0)[0]
+                                 for mlp, tpb, bps in ((8, 256, 8), (16, 256, 4), (4, 512, 4)))
+            gather["l2"] = max(kmers.gather_bench(32 << 20, mlp, tpb, bps, 256, 0)[0]
+                               for mlp, tpb, bps in ((8, 256, 8), (16, 256, 4), (8, 128, 16)))
+        roofline = classify_rooflines(wl, finfo, windows, passes, runs, total, cls_ms / args.steps, clocks, gather)
+        roofline["kernel_share_of_step"] = cls_ms / res_ms
+        roofline["reference_probes_per_launch"] = probes
+        roofline["reference_probes_per_s"] = probes / (cls_ms / args.steps * 1e-3)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
+            t0 = time.perf_counter()
             kind = cpu_reference_setup(wl)
+            cpu_setup_s = time.perf_counter() - t0
             sample_reads = max(1, int(15e6 / wl["mean_len"]))  # ~15 Mbases: 15-20 s on one core
             sample_reads = min(sample_reads, n_reads)
             nb, dt = cpu_time_reads(0, sample_reads, 1)
             cpu = {"value": nb / dt, "unit": UNIT, "cores": 1, "kind": kind,
                    "sample": f"first {sample_reads} reads ({nb} bases) of the same batch, same full-size "
-                             f"sets, 1 process / 1 thread (the reference as shipped), {dt:.1f} s"}
+                             f"sets (built untimed in {cpu_setup_s:.0f} s), 1 process / 1 thread (the reference as "
+                             f"shipped), {dt:.1f} s"}
             # parity spot check while we are here: the sample's counts equal the GPU's
             lib = _REF["lib"]
             for r in range(0, sample_reads, max(1, sample_reads // 25)):
                 got = lib.count(bytes(bases[offsets[r]:offsets[r + 1]]), _REF["A"], _REF["B"])
                 assert got == (ca[r], cb[r]), f"parity failure on read {r}: cpu {got} gpu {(ca[r], cb[r])}"
+            orc = _REF.pop("orc")
+            orc.set_free(_REF.pop("A"))
+            orc.set_free(_REF.pop("B"))
         d2h = n_reads * (4 + 4 + 8 + 8 + 1)
         ascii_h2d = total + 8 * (n_reads + 1)
+
+        def rate(ms):
+            return total_all / (ms / args.steps * 1e-3)
+
         e2e_variants = {
-            "ascii_device_pack": {
-                "value": total_all / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": ascii_h2d, "d2h_bytes_per_step": d2h,
-                "api": "tb_classifier_submit/wait (C ABI): ASCII reads in pinned host memory -> H2D 1 B/base -> "
-                       "k_pack on the device -> classify -> D2H; 2 slots in flight"},
-            "ascii_host_pack": {
-                "value": total_all / (e2e_hostpack_ms / args.steps * 1e-3), "unit": UNIT,
-                "ms_per_step": e2e_hostpack_ms / args.steps,
+            "packed": {
+                "value": rate(e2e_packed_ms), "unit": UNIT, "ms_per_step": e2e_packed_ms / args.steps,
                 "h2d_bytes_per_step": pbs[0].h2d_bytes, "d2h_bytes_per_step": d2h,
-                "api": f"ASCII reads in pinned host memory -> tb_pack_reads on {host_threads} host threads INSIDE the "
-                       "timed region -> tb_classifier_submit_packed (H2D 0.25 B/base) -> classify -> D2H"},
-            "ascii_hybrid": {
-                "value": total_all / (e2e_hybrid_ms / args.steps * 1e-3), "unit": UNIT,
-                "ms_per_step": e2e_hybrid_ms / args.steps,
-                "h2d_bytes_per_step": (ascii_h2d + hyb_n * pbs[0].h2d_bytes) // (1 + hyb_n),
-                "d2h_bytes_per_step": d2h,
-                "cycle": f"1 ASCII : {hyb_n} host-packed",
-                "ms_per_batch_by_cycle": {f"1:{n}": round(v, 4) for n, v in hybrid.items()},
-                "api": "ASCII reads in pinned host memory; in every cycle one batch takes the ASCII route "
-                       f"(tb_classifier_submit) and {hyb_n} take the host-pack route (tb_pack_reads on {host_threads} "
-                       "threads + tb_classifier_submit_packed), each in its own slot, all inside the timed region: "
-                       "PCIe link and host cores work in parallel"},
+                "api": "tb_classifier_submit_packed/wait (C ABI): pinned 2-bit batches as the native pipeline's packer "
+                       "emits them (tb_pack_reads) -> H2D 0.25 B/base -> index + classify + fix-up + decide -> D2H; "
+                       "2 slots in flight"},
+            "ascii_device_pack": {
+                "value": rate(e2e_ascii_ms), "unit": UNIT, "ms_per_step": e2e_ascii_ms / args.steps,
+                "h2d_bytes_per_step": ascii_h2d, "d2h_bytes_per_step": d2h,
+                "api": "tb_classifier_submit/wait: ASCII reads in pinned host memory -> H2D 1 B/base -> k_pack on the "
+                       "device -> classify -> D2H; 2 slots in flight"},
+            "ascii_host_pack": {
+                "value": rate(e2e_hostpack_ms), "unit": UNIT, "ms_per_step": e2e_hostpack_ms / args.steps,
+                "h2d_bytes_per_step": pbs[0].h2d_bytes, "d2h_bytes_per_step": d2h,
+                "api": f"ASCII reads in host memory -> tb_pack_reads on {host_threads} host threads INSIDE the "
+                       "timed region -> tb_classifier_submit_packed -> classify -> D2H (what the native pipeline "
+                       "does per batch)"},
         }
-        best = max(e2e_variants, key=lambda name: e2e_variants[name]["value"])
-        e2e_best = dict(e2e_variants[best], route=best)
         line = {
-            "metric": METRIC, "value": total_all / (res_ms_max / args.steps * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "metric": METRIC, "value": rate(res_ms_max), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": res_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": workload_config(args, wl),
-            "e2e": e2e_best,
+            "config": workload_config(args, wl, world),
+            "e2e": dict(e2e_variants["packed"], route="packed", clocks=clocks_e2e),
             "e2e_variants": e2e_variants,
-            "e2e_packed": {"value": total_all / (e2e_packed_ms / args.steps * 1e-3), "unit": UNIT,
-                           "h2d_bytes_per_step": pbs[0].h2d_bytes, "d2h_bytes_per_step": n_reads * (4 + 4 + 8 + 8 + 1),
-                           "ms_per_step": e2e_packed_ms / args.steps,
-                           "api": "tb_classifier_submit_packed: 2-bit batches packed by tb_pack_reads, already in "
-                                  "pinned host memory when the timed region starts (packing is reported in host_pack)"},
             "host_pack": {"value": total / pack_s, "unit": UNIT, "threads": host_threads,
-                          "what": "tb_pack_reads (AVX-512/AVX2, multi-threaded): ASCII -> 2-bit pinned batch, this rank, mean of 10 calls"},
+                          "what": "tb_pack_reads (AVX-512/AVX2, multi-threaded): ASCII -> 2-bit pinned batch, this rank, mean of 5 calls"},
             "gpu_launches": 5 * args.steps,
-            "value_l2_flushed": total_all / (flush_ms_max / args.steps * 1e-3),
-            "value_sampler_off": total_all / (quiet_ms_max / args.steps * 1e-3),
+            "value_l2_flushed": rate(flush_ms_max),
+            "value_sustained": {"value": total_all / (sus_ms_max / sus_iters * 1e-3), "unit": UNIT, "steps": sus_iters,
+                                "seconds": sus_ms_max * 1e-3, "kernel_only": total / (sus_cls_ms / sus_iters * 1e-3),
+                                "clocks": clocks_sus},
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "probes_per_s": probes_all / (res_ms_max / args.steps * 1e-3),
             "set_build_ms": build_ms,
+            "pair_and_bitmap_build_ms": finfo["build_ms"],
             "setup_s": setup_s,
             "cpu_affinity": f"{len(numa)} cpus next to the GPU (NVML)" if numa else "unchanged",
             "bins": {"A": int((bins == 65).sum()), "B": int((bins == 66).sum()), "U": int((bins == 85).sum())},
         }
-        print(json.dumps(line), flush=True)
+        if world == 1 and not args.no_pipeline:
+            line["pipeline"] = run_pipeline_leg(kmers, synth, A, B, k, wl["keys_a"], wl["keys_b"], args.pipeline_gbases)
     clf.close()
+    kmers.destroy_kmer_hash_set(A)
+    kmers.destroy_kmer_hash_set(B)
+    if rank == 0:
+        if world == 1 and not args.no_other_workloads:
+            del wl, bases, offsets
+            others = {}
+            for name in ("c2", "c4", "c5"):
+                if name != args.workload:
+                    others[name] = run_other_workload(name, kmers, synth, args, gather)
+            line["other_workloads"] = others
+        print(json.dumps(line), flush=True)
     dist.close()
     return 0
 
@@ -667,12 +745,15 @@ def run_gpu_arm(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true")
+    ap.add_argument("--pipeline-gbases", type=float, default=1.0)
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     if args.impl == "reference":

@@ -266,10 +266,46 @@ int tb_crc32_accelerated(void);
 int64_t tb_fastq_gzip(const void *data, int64_t n, void *out_buf, int64_t out_cap, int verify);
 /* Copy in_fd to the gzip file out_path through the pipeline's output writer: text cut into chunks
  * that n_threads workers compress as independent gzip members, written in order, `piece` bytes
- * appended at a time; fastq_encoder != 0 tries the FASTQ-aware encoder before zlib.  Returns the
+ * appended at a time; fastq_encoder 1 tries the FASTQ-aware encoder before zlib, 2 writes BGZF
+ * (<= 64 KiB members with a 'BC' extra field, what bgzip/htslib produce) at `level`.  Returns the
  * number of input bytes or < 0 (testing aid; no GPU involved; the reference writes through
  * Python's gzip.open, seq.py:132-134). */
 int64_t tb_gzip_copy(int in_fd, const char *out_path, int level, int n_threads, int fastq_encoder, int64_t piece);
+
+/* ------------------------------------------------------------------------
+ * (3) find-unique-kmers on the GPU: what the reference gets from the KMC
+ * binaries (src/trio_binning/find_unique_kmers.py:62-233) -- canonical k-mer counting, the
+ * count histogram, set subtraction and the count-range dump.  KMC's documented semantics are
+ * restated: canonical = the lexicographically smaller of a k-mer and its reverse complement;
+ * windows with anything but A/C/G/T (either case) are skipped; counts saturate at
+ * `counter_max` (KMC -cs, 255) and k-mers with fewer than `db_min` occurrences (KMC -ci, 2)
+ * are not in a database.  Keys are MSB-first 2-bit encodings of the canonical string (first base
+ * in the top digit of 2k bits): their integer order is the order KMC dumps in.
+ * ---------------------------------------------------------------------- */
+typedef struct tb_kmer_counter tb_kmer_counter;
+/* A counting table of n_slots (key, count) slots on `device`.  Only keys of partition `part`
+ * of `n_parts` are counted (1 partition = everything): libraries whose distinct k-mers exceed
+ * one table are counted in several passes over the input.  replaces `kmc -k..` (:62-103) */
+tb_kmer_counter *tb_counter_create(int k, uint64_t n_slots, int part, int n_parts, int device);
+void tb_counter_destroy(tb_kmer_counter *c);
+/* Count the canonical k-mers of a batch of reads (concatenated ASCII + offsets, host memory).
+ * Returns once the batch is on its way to the device; the caller may reuse its buffers. */
+int tb_counter_add_batch(tb_kmer_counter *c, const char *bases, const int64_t *offsets, int64_t n_reads);
+/* Count a whole FASTA/FASTQ(.gz) file through the native reader (readfq's records). */
+int tb_counter_add_fastx(tb_kmer_counter *c, const char *reads_path, int64_t batch_bases, int n_threads,
+                         uint64_t *n_reads, uint64_t *n_bases);
+/* Waits for the counting; windows counted, distinct k-mers, table size.  < 0 if the table
+ * filled up (results are then incomplete). */
+int tb_counter_stats(tb_kmer_counter *c, uint64_t *n_windows, uint64_t *n_distinct, uint64_t *n_slots);
+/* hist[i] = number of distinct k-mers seen i times, the last bin collecting everything at or
+ * above n_bins-1 (n_bins = 256 gives KMC's saturated counters).  replaces `kmc_tools transform
+ * .. histogram` (:106-168), whose file starts at count 2 */
+int tb_counter_histogram(tb_kmer_counter *c, uint64_t *hist, int n_bins);
+/* K-mers of a's database that are not in b's (b may be NULL) and whose saturated count lies in
+ * [min_count, max_count]: `kmc_tools simple a b kmers_subtract` + `kmc_dump -ci -cx`
+ * (:171-233).  Stores up to `cap` keys (unordered) and returns how many qualify. */
+int64_t tb_counter_select_unique(tb_kmer_counter *a, tb_kmer_counter *b, uint32_t min_count, uint32_t max_count,
+                                 uint32_t db_min, uint32_t counter_max, uint64_t *out_keys, uint64_t cap);
 
 /* Timing marks: record CUDA event `which` (0 or 1) on the slot's stream at the
  * current point of its queue; elapsed() waits for the `to` mark and returns the
@@ -291,6 +327,10 @@ int tb_classifier_rerun_resident_flush(tb_classifier *c, int slot, int iters, ui
 /* Number of windows of the slot's last batch whose pre-filter bit was set (they are the
  * only ones that probed the tables in HBM); 0 when the direct kernel is in use. */
 int tb_classifier_filter_passes(tb_classifier *c, int slot, uint64_t *n_pass);
+/* Measurement aid for the roofline: the number of bitmap SECTOR fetches the slot's last batch
+ * needs when each lane of the classify kernel re-uses a sector across the consecutive windows
+ * that share it (minimizer-addressed bitmap; = windows otherwise).  Runs its own kernel. */
+int tb_classifier_sector_runs(tb_classifier *c, int slot, uint64_t *n_runs);
 /* The classifier's bitmap pre-filter: log2 of its size in bits (0 = none, the direct
  * kernel is used) and the device time spent building it and the pair table. */
 int tb_classifier_filter_info(tb_classifier *c, int *log2_bits, float *build_ms);

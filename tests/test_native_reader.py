@@ -261,3 +261,23 @@ def test_line_endings_across_the_4_mib_chunks_of_the_read_ahead(kmers, seq, tmp_
         with gzip.open(gz, "wb", compresslevel=1) as f:
             f.write(raw)
         assert kmers.fastx_dump(str(gz)) == want, flavour + " (gz)"
+
+
+def test_bgzf_writer_round_trip(kmers, tmp_path):
+    """tb_gzip_copy's BGZF mode (input generator for benchmarks): valid gzip for Python, BGZF for
+    the parallel reader, identical text."""
+    import gzip
+
+    recs, text = _fastq_text(400, 3000, 31)
+    src = tmp_path / "in.fastq"
+    src.write_bytes(text)
+    out = tmp_path / "out.fastq.gz"
+    kmers.gzip_copy(str(src), str(out), level=6, threads=3, bgzf=True, piece=100_000)
+    blob = out.read_bytes()
+    assert blob[:4] == b"\x1f\x8b\x08\x04" and blob[12:14] == b"BC"
+    assert gzip.decompress(blob) == text
+    assert kmers.fastx_dump(str(out)) == recs
+    empty = tmp_path / "empty.fastq"
+    empty.write_bytes(b"")
+    kmers.gzip_copy(str(empty), str(tmp_path / "e.gz"), bgzf=True)
+    assert gzip.decompress((tmp_path / "e.gz").read_bytes()) == b""

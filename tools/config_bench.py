@@ -78,18 +78,25 @@ def main():
         from trio_binning_b200 import synth
 
         for k in range(13, 32):
-            run("ksweep", k, 10_000_000, 10_000_000, args.reads or 10_000, 20_000, False, args.iters,
+            n = min(10_000_000, 4 ** k // 16)  # k = 13, 14: the k-mer space is too small for 10 M + 10 M
+            run("ksweep", k, n, n, args.reads or 10_000, 20_000, False, args.iters,
                 args.plant_every or 1000, label=f"k{k}")
         return
     if args.what == "density":
-        # throughput against hit density: one planted k-mer per P bases (about half findable)
+        # throughput against hit density: the sets are ALL k-mers of two 10-Mbase random genomes
+        # (canonical orientation: every one findable), the reads carry pieces of their
+        # haplotype's genome over a chosen fraction of their length
         from trio_binning_b200 import synth
 
         k, n_a, n_b, n_reads, mean_len, fixed = CONFIGS["c2"]
-        sets = synth.sorted_disjoint_sets(n_a, n_b, k, seed=1000 + k)
-        for p in (2000, 200, 20, 4, 2):
-            run("c2", k, n_a, n_b, args.reads or n_reads, mean_len, fixed, args.iters, p, sets=sets,
-                label=f"c2_plant_every_{p}")
+        rng = np.random.default_rng(77)
+        letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+        ga, gb = letters[rng.integers(0, 4, size=n_a + k - 1)], letters[rng.integers(0, 4, size=n_b + k - 1)]
+        sets = (synth.genome_kmer_set(ga, k), synth.genome_kmer_set(gb, k))
+        for f in (0.0, 0.001, 0.01, 0.1, 0.5, 1.0):
+            reads = synth.mosaic_reads(args.reads or n_reads, mean_len, k, ga, gb, seed=5, fraction=f)[:2]
+            run("c2", k, n_a, n_b, args.reads or n_reads, mean_len, fixed, args.iters, 0, sets=sets,
+                label=f"c2_genome_sets_fraction_{f}", repeat_reads=reads)
         # low-complexity reads: short tandem repeats (period 1..6) -- few distinct minimizers,
         # every window of a repeat maps to the same few bitmap sectors
         rng = np.random.default_rng(5)

@@ -12,7 +12,7 @@ from importlib.machinery import EXTENSION_SUFFIXES
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-SOURCES = ["capi.cu", "set_build.cu", "classify.cu", "gather_bench.cu", "host_pack.cpp",
+SOURCES = ["capi.cu", "capi_count.cu", "set_build.cu", "classify.cu", "kmer_count.cu", "gather_bench.cu", "host_pack.cpp",
            "fastx_pipeline.cpp", "gz_stream.cpp", "fastq_deflate.cpp"]
 HEADERS = ["kmer_device.cuh", "launchers.h", "gz_stream.h", "fastq_deflate.h", os.path.join("..", "..", "include", "trio_kmers_b200.h")]
 LIB_NAME = "kmers_c" + EXTENSION_SUFFIXES[0]

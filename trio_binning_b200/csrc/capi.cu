@@ -502,6 +502,11 @@ extern "C" {
 const char *tb_last_error(void) { return g_err.c_str(); }
 // for the other translation units of the library (not part of the public header)
 void tb_internal_set_error(const char *message) { g_err = message ? message : ""; }
+int tb_internal_use_device(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return use_device(device);
+}
 const char *tb_version(void) { return "trio_kmers_b200 0.1 (sm_100a)"; }
 
 int tb_device_count(void)
@@ -1034,6 +1039,32 @@ int tb_classifier_filter_passes(tb_classifier *c, int slot, uint64_t *n_pass)
     unsigned long long v = 0;
     CK(cudaMemcpy(&v, s.d_n_pass, sizeof v, cudaMemcpyDeviceToHost));
     if (n_pass) *n_pass = c->d_filter ? v : 0;
+    return 0;
+}
+
+int tb_classifier_sector_runs(tb_classifier *c, int slot, uint64_t *n_runs)
+{
+    if (!c) return fail("null classifier");
+    if (slot < 0 || slot >= (int)c->slots.size()) return fail("slot %d out of range", slot);
+    CK(cudaSetDevice(c->device));
+    Slot &s = c->slots[(size_t)slot];
+    if (!s.view.F || s.view.n_reads == 0) return fail("no batch in slot %d", slot);
+    CK(cudaStreamSynchronize(s.stream));
+    if (!(c->d_pair && c->d_filter && c->mini)) {
+        // hash-addressed bitmap or no bitmap: nothing is shared between windows
+        if (n_runs) *n_runs = s.windows;
+        return 0;
+    }
+    unsigned long long *d = nullptr;
+    DeviceScratch guard;
+    CK(cudaMalloc((void **)&d, sizeof *d));
+    guard.mem.push_back(d);
+    CK(cudaMemsetAsync(d, 0, sizeof *d, s.stream));
+    CK(tb_launch_count_sector_runs(s.view, c->k, (c->filter_word_mask >> 3) + 1, d, s.stream));
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, d, sizeof v, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    if (n_runs) *n_runs = v;
     return 0;
 }
 

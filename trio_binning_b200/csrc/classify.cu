@@ -92,6 +92,11 @@ k_pack(tb_batch_view b, int k)
         const uint4 *src = reinterpret_cast<const uint4 *>(b.ascii + p0);
         uint4 q0 = __ldg(src), q1 = __ldg(src + 1);
         uint32_t x[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+        if (b.fold_case) {
+            // k-mer counting: clearing bit 5 turns a, c, g, t into A, C, G, T and no other byte into a base
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] &= 0xDFDFDFDFu;
+        }
         // Fast path: take the two code bits of every byte as if it were a base, rebuild the
         // letter those bits stand for (A 0x41, C 0x43, G 0x47, T 0x54 = 0x41 + 2c + 2*[c>=2]
         // + 11*[c==3], four bytes at a time, no carries) and compare with the input: any
@@ -121,6 +126,7 @@ k_pack(tb_batch_view b, int k)
         int n = (int)(b.total_bases - p0);
         for (int i = 0; i < n; i++) {
             unsigned char c = b.ascii[p0 + i];
+            if (b.fold_case) c &= 0xDFu;
             if (tb_base_valid(c))
                 f |= (uint64_t)tb_base_code(c) << (2 * i);
             else
@@ -128,6 +134,12 @@ k_pack(tb_batch_view b, int k)
         }
     }
     b.F[w] = f;
+    if (b.V) {
+        // k-mer counting wants the validity bits themselves; the fill-forward stream and the
+        // Q3-UB bookkeeping below belong to the classify path only
+        b.V[w] = vmask;
+        return;
+    }
     const bool is_dirty = vmask != 0xFFFFFFFFu;
     if (is_dirty) {
         // rare path: fill-forward stream + Q3-UB flagging
@@ -624,22 +636,42 @@ k_pair_filter_build(const unsigned long long *__restrict__ slots, uint64_t n_slo
 // (15/16) that many minimizer values share a sector, which evens out the skew of minimizer
 // popularity.  The minimizer is a pure function of the key VALUE, so stored keys (raw, Q1)
 // and looked-up keys agree whatever strand or scratch quirk produced them.
-// m: 16 for k >= 22, else k-6 but at least k/2 so that the first and the last m-mer of a
-// k-mer together cover all of its bases (their hashes also address the word and the bits)
-__host__ __device__ __forceinline__ int tb_minimizer_m(int k)
+// m: 16 for k >= 22; below that k-6 (seven m-mers per window), but not less than 13 while that
+// leaves three m-mers per window -- with fewer than ~4^13 / 2 distinct minimizers the keys of a
+// 10 M + 10 M set crowd into a fraction of the bitmap's sectors and a third to nine tenths of all
+// windows pass it (measured at k = 15 .. 17 with m = k - 6: profiles/r2_ksweep_before_m13.jsonl)
+// -- and never less than k/2, so that the first and the last m-mer of a k-mer together cover all
+// of its bases (their hashes also address the word and the bits)
+__host__ __device__ constexpr int tb_minimizer_m(int k)
 {
     if (k >= 22) return 16;
-    const int a = k - 6, b = (k + 1) / 2;
-    return a > b ? a : b;
+    int m = k - 6;
+    const int floor13 = k - 2 < 13 ? k - 2 : 13;
+    if (m < floor13) m = floor13;
+    const int half = (k + 1) / 2;
+    return m > half ? m : half;
 }
 
+#ifndef TB_MIX
+#define TB_MIX 0
+#endif
 __device__ __forceinline__ uint32_t mmer_mix(uint32_t c)
 {
+#if TB_MIX == 0
     c *= 0x9E3779B1u;
     c ^= c >> 15;
     c *= 0x85EBCA77u;
     c ^= c >> 13;
     return c;
+#else
+    // multiply-fold: the 64-bit product of the m-mer and an odd constant, high half xor low half,
+    // twice.  Each round is one IMAD.WIDE (FMA pipe) and one LOP3 where the xor-shift round above
+    // needs a shift and a xor on the ALU pipe, the pipe that bounds the kernel
+    uint64_t p = (uint64_t)c * 0x9E3779B1u;
+    c = (uint32_t)p ^ (uint32_t)(p >> 32);
+    p = (uint64_t)c * 0x85EBCA77u;
+    return (uint32_t)p ^ (uint32_t)(p >> 32);
+#endif
 }
 
 // reverse complement of an m-mer held in the low 2m bits
@@ -657,6 +689,12 @@ __device__ __forceinline__ uint32_t mmer_revcomp(uint32_t f, int m)
 //             symmetric under reverse complement (first and last swap), and in the kernel both
 //             terms are already in the sliding window of m-mer hashes: phase 1 needs no k-mer
 //             key at all, only m-mers.
+// TB_MSCALE=1: the canonical m-mer is hashed as min(f, r) << (32 - 2m) -- the same order, so the
+// same minimum -- which lets the kernel drop an m-mer's two unused top bits with a multiply (FMA
+// pipe) instead of masking them off (ALU pipe).  m = 16 needs neither.
+#ifndef TB_MSCALE
+#define TB_MSCALE 1
+#endif
 struct KmerCoord {
     uint32_t min_hash, fh;
 };
@@ -670,7 +708,11 @@ __device__ __forceinline__ KmerCoord coord_of_key(uint64_t key, int k, int m)
     for (int i = 0; i + m <= k; i++) {
         const uint32_t f = (uint32_t)(key >> (2 * i)) & mmask;
         const uint32_t r = mmer_revcomp(f, m);
+#if TB_MSCALE
+        const uint32_t h = mmer_mix((f < r ? f : r) << (32 - 2 * m));
+#else
         const uint32_t h = mmer_mix(f < r ? f : r);
+#endif
         c.min_hash = h < c.min_hash ? h : c.min_hash;
         if (i == 0) first = h;
         last = h;
@@ -689,6 +731,25 @@ __device__ __forceinline__ KmerCoord coord_of_key(uint64_t key, int k, int m)
 __device__ __forceinline__ uint32_t mini_word_index(uint32_t min_hash, uint32_t fh, uint32_t n_sectors)
 {
     return __umulhi(min_hash * 0xC2B2AE35u, n_sectors) * 8u + __umulhi(fh * 0x9E3779B1u, 8u);
+}
+
+// The bits a k-mer sets in its bitmap word.  TB_BITTEST=1 takes the second position from the product
+// that already selects the word (bits 24..28 of fh * 0x9E3779B1; bits 29..31 are the word), so that
+// the kernel can test "both bits set" with two wrapping shifts of the loaded word and one LOP3
+// instead of building a two-bit mask first.
+#ifndef TB_BITTEST
+#define TB_BITTEST 0
+#endif
+template <int NBITS>
+__device__ __forceinline__ uint32_t mini_need(uint32_t fh)
+{
+#if TB_BITTEST == 0
+    return filter_bits<NBITS>(fh);
+#else
+    uint32_t m = __funnelshift_l(0u, 1u, fh);
+    if (NBITS == 2) m |= __funnelshift_l(0u, 1u, (fh * 0x9E3779B1u) >> 24);
+    return m;
+#endif
 }
 
 __device__ __forceinline__ uint32_t ld_filter_l1(const uint32_t *p, uint64_t policy)
@@ -732,7 +793,7 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
 {
     const int k = K ? K : k_runtime;
     const int m = tb_minimizer_m(k);
-    constexpr int MC = K ? (K >= 22 ? 16 : K - 6) : 1;   // compile-time m for the unrolled path
+    constexpr int MC = K ? tb_minimizer_m(K) : 1;        // compile-time m for the unrolled path
     constexpr int WC = K ? K - MC + 1 : 1;               // m-mers per k-mer
     const uint64_t kmask = (1ull << (2 * k)) - 1ull;  // k <= 31
     const int lane = threadIdx.x & 31;
@@ -750,14 +811,39 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
             // Two passes of 16 windows over the same unrolled body (the second on the span
             // moved by 16 bases) keep the loop inside the instruction cache.
             constexpr uint32_t MMASK = MC == 16 ? 0xFFFFFFFFu : ((1u << (2 * MC)) - 1u);
+            constexpr uint32_t MSCALE = 1u << (32 - 2 * MC);
+            (void)MMASK;
+            (void)MSCALE;
             LaneCtx h = c;  // half-span view: window j of the half starts at base j of (f0,f1)
+#ifndef TB_REVODD
+#define TB_REVODD 1  // measured: C3 1.350 -> 1.297 ms, k = 31 at C2 0.543 -> 0.533 ms (profiles/r2_variants_alu.txt)
+#endif
+#if TB_REVODD
+            // Odd lanes walk their 32 windows backwards by working on the other strand: window j of
+            // the reverse-complemented span (moved by 33-K bases) is window 31-j of the lane, and the
+            // bitmap coordinates do not depend on the strand.  A lane's last window then meets its
+            // right neighbour's first window in the SAME load instruction -- they usually share
+            // their minimizer, hence their sector -- instead of missing L1 a second time much later.
+            if (lane & 1) {
+                constexpr int S = K ? 2 * (33 - K) : 2;  // 4 .. 40 bits (K = 0 never takes this path)
+                h.f0 = (c.r_lo >> S) | (c.r_hi << (64 - S));
+                h.f1 = c.r_hi >> S;
+                h.r_hi = (c.f1 << S) | (c.f0 >> (64 - S));
+                h.r_lo = c.f0 << S;
+            }
+#endif
             // m-mer hashes of the first WC-1 positions of a half; the second half inherits them
             // from the first (its positions 16 .. 16+WC-2)
             uint32_t head[WC > 1 ? WC - 1 : 1];
 #pragma unroll
             for (int q = 0; q < WC - 1; q++) {
+#if TB_MSCALE
+                const uint32_t f = (uint32_t)extract128(h.f0, h.f1, 2 * q) * MSCALE;
+                const uint32_t r = (uint32_t)extract128(h.r_lo, h.r_hi, 2 * (64 - q - MC)) * MSCALE;
+#else
                 const uint32_t f = (uint32_t)extract128(h.f0, h.f1, 2 * q) & MMASK;
                 const uint32_t r = (uint32_t)extract128(h.r_lo, h.r_hi, 2 * (64 - q - MC)) & MMASK;
+#endif
                 head[q] = mmer_mix(f < r ? f : r);
             }
 #pragma unroll 1
@@ -769,12 +855,20 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
 #pragma unroll
                 for (int g = 0; g < 16; g += U) {
                     uint32_t need[U], wd[U], widx[U];
+#if TB_BITTEST
+                    uint32_t need2[U];
+#endif
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         const int j = g + u, q = j + WC - 1;
                         {
+#if TB_MSCALE
+                            const uint32_t f = (uint32_t)extract128(h.f0, h.f1, 2 * q) * MSCALE;
+                            const uint32_t r = (uint32_t)extract128(h.r_lo, h.r_hi, 2 * (64 - q - MC)) * MSCALE;
+#else
                             const uint32_t f = (uint32_t)extract128(h.f0, h.f1, 2 * q) & MMASK;
                             const uint32_t r = (uint32_t)extract128(h.r_lo, h.r_hi, 2 * (64 - q - MC)) & MMASK;
+#endif
                             hm[q] = mmer_mix(f < r ? f : r);
                         }
                         uint32_t mn = hm[j];
@@ -782,14 +876,30 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
                         for (int t = 1; t + 1 < WC; t += 2) mn = __vimin3_u32(mn, hm[j + t], hm[j + t + 1]);
                         if ((WC & 1) == 0) mn = min(mn, hm[j + WC - 1]);
                         const uint32_t fh = hm[j] + hm[j + WC - 1];  // first + last m-mer of the window
+#if TB_BITTEST
+                        const uint32_t t = fh * 0x9E3779B1u;
+                        need[u] = fh;                   // shift amounts: the funnel shifts use their low 5 bits
+                        need2[u] = __umulhi(t, 256u);   // t >> 24 on the FMA pipe
+                        widx[u] = __umulhi(mn * 0xC2B2AE35u, n_sectors) * 8u + __umulhi(t, 8u);
+#else
                         need[u] = filter_bits<NBITS>(fh);
                         widx[u] = mini_word_index(mn, fh, n_sectors);
+#endif
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) wd[u] = ld_filter_l1(filter + widx[u], keep_policy);
+#if TB_BITTEST
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        uint32_t bit = __funnelshift_r(wd[u], 0u, need[u]);
+                        if (NBITS == 2) bit &= __funnelshift_r(wd[u], 0u, need2[u]);
+                        half_pass += (bit & 1u) << (g + u);
+                    }
+#else
 #pragma unroll
                     for (int u = 0; u < U; u++)
                         if ((need[u] & ~wd[u]) == 0) half_pass |= 1u << (g + u);
+#endif
                 }
                 pass |= half_pass << (16 * half);
 #pragma unroll
@@ -800,12 +910,15 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
                 h.r_hi = (h.r_hi << 32) | (h.r_lo >> 32);
                 h.r_lo <<= 32;
             }
+#if TB_REVODD
+            if (lane & 1) pass = __brev(pass);
+#endif
         } else {
             // ---- a non-ACGT base nearby (or an unusual k): minimizer from the key itself
             for (int j = 0; j < 32; j++) {
                 if (!((c.vmask >> j) & 1u)) continue;
                 const KmerCoord kc = coord_of_key(window_key<0>(c, j, k, kmask), k, m);
-                const uint32_t need = filter_bits<NBITS>(kc.fh);
+                const uint32_t need = mini_need<NBITS>(kc.fh);
                 const uint32_t wd = ld_filter_l1(filter + mini_word_index(kc.min_hash, kc.fh, n_sectors), keep_policy);
                 pass |= ((wd & need) == need ? 1u : 0u) << j;
             }
@@ -849,6 +962,33 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
     lane_attribute(b, c, lane, hit_a, hit_b);
 }
 
+// Measurement aid (bench.py's roofline; never on the timed path): how many bitmap SECTOR fetches
+// the batch needs when every lane re-uses a sector across consecutive windows that share it --
+// per lane, the number of times the sector changes along its 32 windows.  Same work split and
+// same coordinates as k_classify_pair_mini, computed the slow way from each window's key.
+__global__ void __launch_bounds__(128)
+k_count_sector_runs(tb_batch_view b, int k, uint32_t n_sectors, unsigned long long *out)
+{
+    const int m = tb_minimizer_m(k);
+    const uint64_t kmask = (1ull << (2 * k)) - 1ull;
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= b.n_tiles) return;
+    LaneCtx c;
+    lane_setup(b, tile, lane, k, c);
+    unsigned runs = 0;
+    uint32_t prev = 0xFFFFFFFFu;
+    for (int j = 0; j < 32; j++) {
+        if (!((c.vmask >> j) & 1u)) continue;
+        const KmerCoord kc = coord_of_key(window_key<0>(c, j, k, kmask), k, m);
+        const uint32_t sector = __umulhi(kc.min_hash * 0xC2B2AE35u, n_sectors);
+        if (sector != prev) runs++;
+        prev = sector;
+    }
+    runs = __reduce_add_sync(0xFFFFFFFFu, runs);
+    if (lane == 0 && runs) atomicAdd(out, (unsigned long long)runs);
+}
+
 template <int NBITS>
 __global__ void __launch_bounds__(256)
 k_pair_filter_build_mini(const unsigned long long *__restrict__ slots, uint64_t n_slots, uint32_t *filter,
@@ -859,7 +999,7 @@ k_pair_filter_build_mini(const unsigned long long *__restrict__ slots, uint64_t 
     const unsigned long long e = slots[i];
     if (e == 0) return;
     const KmerCoord kc = coord_of_key(e & TB_PAIR_KEYMASK, k, tb_minimizer_m(k));
-    atomicOr(&filter[mini_word_index(kc.min_hash, kc.fh, n_sectors)], filter_bits<NBITS>(kc.fh));
+    atomicOr(&filter[mini_word_index(kc.min_hash, kc.fh, n_sectors)], mini_need<NBITS>(kc.fh));
 }
 
 // ---- bitmap construction: one thread per table slot ---------------------------------
@@ -1108,6 +1248,14 @@ cudaError_t tb_launch_classify_pair_mini(const tb_batch_view &b, int k, tb_pair_
         }
     }
     return launch_pair_mini_k<0>(b, k, P, filter, n_sectors, n_bits, p2_width, stream);
+}
+
+cudaError_t tb_launch_count_sector_runs(const tb_batch_view &b, int k, uint32_t n_sectors,
+                                        unsigned long long *d_out, cudaStream_t stream)
+{
+    if (b.n_tiles == 0) return cudaSuccess;
+    k_count_sector_runs<<<(unsigned)((b.n_tiles + 3) / 4), 128, 0, stream>>>(b, k, n_sectors, d_out);
+    return cudaGetLastError();
 }
 
 cudaError_t tb_launch_pair_filter_build_mini(const uint64_t *d_pair_table, uint64_t n_slots, uint32_t *filter,

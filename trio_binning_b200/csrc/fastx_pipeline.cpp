@@ -733,6 +733,39 @@ bool gzip_member(const std::string &in, int level, std::string &out)
     return rc == Z_STREAM_END;
 }
 
+// One chunk of text as BGZF (SAM spec 4.1; what bgzip/htslib write): independent gzip members of at
+// most 64 KiB of text, each with a 'BC' extra subfield that holds its compressed size - 1.  Used to
+// make BGZF test and benchmark inputs (the reader decodes such files on several threads).
+bool bgzf_blocks(const std::string &in, int level, std::string &out)
+{
+    out.clear();
+    std::vector<unsigned char> buf(70000);
+    for (size_t off = 0; off < in.size() || off == 0; off += 65280) {
+        const size_t n = std::min<size_t>(65280, in.size() - off);
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+        zs.next_in = (Bytef *)in.data() + off;
+        zs.avail_in = (uInt)n;
+        zs.next_out = buf.data();
+        zs.avail_out = (uInt)buf.size();
+        const int rc = deflate(&zs, Z_FINISH);
+        const size_t clen = zs.total_out;
+        deflateEnd(&zs);
+        if (rc != Z_STREAM_END || clen + 26 > 65536) return false;
+        const size_t total = 18 + clen + 8;
+        const unsigned char head[18] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0,
+                                         (unsigned char)((total - 1) & 0xff), (unsigned char)((total - 1) >> 8) };
+        out.append((const char *)head, 18);
+        out.append((const char *)buf.data(), clen);
+        const uint32_t crc = (uint32_t)crc32(0L, (const Bytef *)in.data() + off, (uInt)n), isize = (uint32_t)n;
+        for (uint32_t v : { crc, isize })
+            for (int b = 0; b < 4; b++) out.push_back((char)((v >> (8 * b)) & 0xff));
+        if (in.empty()) break;
+    }
+    return true;
+}
+
 class Pool {
 public:
     explicit Pool(int n)
@@ -797,6 +830,7 @@ struct GzFileWriter : BinWriter {
     int fd = -1;
     int level = 9;
     bool fastq_encoder = false;  // try the FASTQ-aware encoder first, zlib where it declines
+    bool bgzf = false;           // write BGZF blocks (input generator for tests and benchmarks)
     Pool *pool = nullptr;
     std::atomic<uint64_t> *deflate_ns = nullptr;  // CPU time spent compressing, summed over the pool
     std::string pending;  // uncompressed text not yet dispatched
@@ -816,12 +850,14 @@ struct GzFileWriter : BinWriter {
         auto prom = std::make_shared<std::promise<std::shared_ptr<std::string>>>();
         inflight.push_back(prom->get_future().share());
         const int lvl = level;
-        const bool fq = fastq_encoder;
+        const bool fq = fastq_encoder, bg = bgzf;
         std::atomic<uint64_t> *ns = deflate_ns;
-        pool->submit([in, prom, lvl, fq, ns] {
+        pool->submit([in, prom, lvl, fq, bg, ns] {
             const auto t0 = Clock::now();
             auto out = std::make_shared<std::string>();
-            if (!(fq && tb::fastq_gzip_member(in->data(), in->size(), *out, true)) && !gzip_member(*in, lvl, *out))
+            if (bg) {
+                if (!bgzf_blocks(*in, lvl, *out)) out->clear();
+            } else if (!(fq && tb::fastq_gzip_member(in->data(), in->size(), *out, true)) && !gzip_member(*in, lvl, *out))
                 out->clear();
             if (ns) ns->fetch_add((uint64_t)(seconds_since(t0) * 1e9));
             prom->set_value(out);
@@ -1524,6 +1560,48 @@ int tb_route_fastx(const char *reads_path, const char *bins, int64_t n_bins, int
     return run_pipeline(cfg, stats);
 }
 
+// find-unique-kmers: every record of a FASTA/FASTQ(.gz) file through the k-mer counter
+int tb_counter_add_fastx(tb_kmer_counter *counter, const char *reads_path, int64_t batch_bases, int n_threads,
+                         uint64_t *n_reads, uint64_t *n_bases)
+{
+    if (!counter || !reads_path) return -1;
+    Reader reader;
+    reader.batch_bases = std::max<int64_t>(1, batch_bases);
+    int threads = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    reader.src.set_threads(std::max(1, std::min(6, threads / 2)));
+    if (!reader.src.open(reads_path, reader.error)) {
+        tb_internal_set_error(reader.error.c_str());
+        return -2;
+    }
+    BatchQueue free_q, full_q;
+    reader.free_q = &free_q;
+    reader.full_q = &full_q;
+    std::vector<std::unique_ptr<Batch>> batches;
+    for (int i = 0; i < 3; i++) {
+        batches.emplace_back(new Batch());
+        batches.back()->pinned = false;
+        if (!batches.back()->grow_bases(std::min<int64_t>(reader.batch_bases, 64 << 20) + (1 << 20))) return -3;
+        free_q.push(batches.back().get());
+    }
+    std::thread t([&] { reader.run(); });
+    int rc = 0;
+    for (;;) {
+        Batch *b = full_q.pop();
+        if (rc == 0 && b->n() > 0 && tb_counter_add_batch(counter, b->bases, b->offsets.data(), b->n()) != 0) rc = -5;
+        const bool last = b->last;
+        free_q.push(b);
+        if (last) break;
+    }
+    t.join();
+    if (!reader.error.empty()) {
+        tb_internal_set_error(reader.error.c_str());
+        rc = rc ? rc : -10;
+    }
+    if (n_reads) *n_reads = reader.n_reads;
+    if (n_bases) *n_bases = reader.n_bases;
+    return rc;
+}
+
 // exposed for tests: Python's repr(float) as implemented above
 int tb_float_repr(double x, char *buf, int buf_len)
 {
@@ -1602,8 +1680,9 @@ int64_t tb_gzip_copy(int in_fd, const char *out_path, int level, int n_threads, 
     GzFileWriter w;
     w.pool = &pool;
     w.level = level;
-    w.fastq_encoder = fastq_encoder != 0;
-    w.max_inflight = 3;  // exercise the back-pressure path
+    w.fastq_encoder = fastq_encoder == 1;
+    w.bgzf = fastq_encoder == 2;
+    w.max_inflight = (size_t)std::max(3, 2 * n_threads);  // small: exercises the back-pressure path
     if (!w.open(out_path)) return -2;
     std::vector<char> buf((size_t)piece);
     int64_t total = 0;

@@ -9,6 +9,8 @@
 //   variant 1: two 128-bit loads of the same sector
 //   variant 2: one 64-bit load per sector (touches the sector, moves 8 bytes to the SM)
 //   variant 3/4: all 2/4 sectors of one random aligned 64-B / 128-B block (rate = blocks/s)
+//   variant 13: one 32-bit load per sector, allocating in L1, evict_last in L2 -- the classify
+//               kernel's bitmap load
 #include "launchers.h"
 
 namespace {
@@ -57,7 +59,7 @@ __global__ void k_gather(const tb_bucket *__restrict__ buf, uint64_t n_sectors, 
     uint64_t policy = 0;
     if (VARIANT == 9)
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    if (VARIANT == 10)
+    if (VARIANT == 10 || VARIANT == 13)
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
     for (int s = 0; s < steps; s++) {
         uint64_t idx[MLP];
@@ -88,6 +90,14 @@ __global__ void k_gather(const tb_bucket *__restrict__ buf, uint64_t n_sectors, 
             }
 #pragma unroll
             for (int u = 0; u < MLP; u++) acc ^= v[u][0].x ^ v[u][0].y ^ v[u][1].x ^ v[u][1].y;
+        } else if (VARIANT == 13) {
+            uint32_t v[MLP];
+#pragma unroll
+            for (int u = 0; u < MLP; u++)
+                asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;"
+                             : "=r"(v[u]) : "l"(reinterpret_cast<const uint32_t *>(buf + idx[u]) + (state & 7u)), "l"(policy));
+#pragma unroll
+            for (int u = 0; u < MLP; u++) acc ^= v[u];
         } else if (VARIANT == 3 || VARIANT == 4) {
             // SPAN adjacent sectors of one aligned 64-B (3) or 128-B (4) block per unit:
             // does DRAM hand out the neighbours for free?
@@ -156,6 +166,7 @@ cudaError_t tb_launch_gather(const void *d_buf, uint64_t n_sectors, int loads_in
     case 10: return launch_v<10>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
     case 11: return launch_v<11>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
     case 12: return launch_v<12>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
+    case 13: return launch_v<13>(buf, n_sectors, loads_in_flight, threads_per_block, blocks, steps, d_sink, stream);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -59,7 +59,28 @@ struct tb_batch_view {
     double *score_a;
     double *score_b;
     char *bin;
+    // k-mer counting (kmer_count.cu) only: V = one validity bit per base (word i/32, bit i%32),
+    // written by k_pack when not null; fold_case: a, c, g, t count as bases (KMC's reading of
+    // FASTA/FASTQ; the classify path keeps the reference's upper-case-only rule, c/kmers.c:56-68)
+    uint32_t *V;
+    int fold_case;
 };
+
+// ---- k-mer counting (kmer_count.cu) --------------------------------------------------------
+struct tb_count_view {
+    unsigned long long *keys;  // canonical k-mers, MSB-first, empty = ~0
+    uint32_t *counts;
+    uint64_t n_slots;
+    uint32_t part, n_parts;    // only keys of partition `part` of `n_parts` are counted
+};
+// stats[0] += windows counted, stats[1] += new distinct keys, stats[2] |= table full
+cudaError_t tb_launch_count_windows(const uint64_t *d_F, const uint32_t *d_V, const int64_t *d_offsets, int64_t n_reads,
+                                    int64_t total_bases, int k, tb_count_view T, unsigned long long *d_stats,
+                                    cudaStream_t stream);
+cudaError_t tb_launch_count_histogram(tb_count_view T, unsigned long long *d_hist, int n_bins, cudaStream_t stream);
+cudaError_t tb_launch_count_select(tb_count_view A, tb_count_view B, uint32_t min_count, uint32_t max_count,
+                                   uint32_t db_min, uint32_t counter_max, unsigned long long *d_out,
+                                   unsigned long long cap, unsigned long long *d_n_out, cudaStream_t stream);
 
 cudaError_t tb_launch_pack(const tb_batch_view &b, int k, cudaStream_t stream);
 cudaError_t tb_launch_index(const tb_batch_view &b, int k, cudaStream_t stream);
@@ -87,6 +108,9 @@ cudaError_t tb_launch_pair_filter_build(const uint64_t *d_pair_table, uint64_t n
 cudaError_t tb_launch_classify_pair_mini(const tb_batch_view &b, int k, tb_pair_view P,
                                          const uint32_t *filter, uint32_t n_sectors, int n_bits,
                                          int p2_width, cudaStream_t stream);
+// measurement aid: bitmap sector fetches of the batch with per-lane re-use (adds to *d_out)
+cudaError_t tb_launch_count_sector_runs(const tb_batch_view &b, int k, uint32_t n_sectors,
+                                        unsigned long long *d_out, cudaStream_t stream);
 cudaError_t tb_launch_pair_filter_build_mini(const uint64_t *d_pair_table, uint64_t n_slots, uint32_t *filter,
                                              uint32_t n_sectors, int n_bits, int k, cudaStream_t stream);
 cudaError_t tb_launch_fixup(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,

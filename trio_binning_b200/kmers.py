@@ -138,6 +138,7 @@ lib.tb_classifier_rerun_resident.argtypes = [C.c_void_p, C.c_int, C.c_int,
 lib.tb_classifier_rerun_resident_flush.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64,
                                                    C.POINTER(C.c_float), C.POINTER(C.c_float)]
 lib.tb_classifier_filter_passes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+lib.tb_classifier_sector_runs.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
 lib.tb_classifier_minimizer_mode.argtypes = [C.c_void_p]
 lib.tb_classifier_pair_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
 lib.tb_classifier_filter_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
@@ -573,6 +574,12 @@ class Classifier:
         _check(lib.tb_classifier_filter_passes(self._h, slot, C.byref(n)))
         return n.value
 
+    def sector_runs(self, slot: int) -> int:
+        """Bitmap sector fetches of the slot's last batch with per-lane re-use (roofline aid)."""
+        n = C.c_uint64()
+        _check(lib.tb_classifier_sector_runs(self._h, slot, C.byref(n)))
+        return n.value
+
     def filter_info(self) -> dict:
         """log2(bits) of the L2-resident pre-filter (0 = direct kernel) and its build time."""
         m, ms = C.c_int(), C.c_float()
@@ -787,10 +794,12 @@ def fastq_gzip(text: bytes, verify: bool = True) -> Optional[bytes]:
 
 
 def gzip_copy(in_path: str, out_path: str, level: int = 6, threads: int = 2, fastq_encoder: bool = False,
-              piece: int = 1 << 16) -> int:
-    """Compress a file with the native pipeline's output writer (testing aid, no GPU needed)."""
+              piece: int = 1 << 16, bgzf: bool = False) -> int:
+    """Compress a file with the native pipeline's output writer: 4 MiB chunks as independent gzip
+    members, or BGZF blocks with bgzf=True (testing / benchmarking aid, no GPU needed)."""
     with open(in_path, "rb") as f:
-        n = lib.tb_gzip_copy(f.fileno(), os.fsencode(out_path), level, threads, 1 if fastq_encoder else 0, piece)
+        n = lib.tb_gzip_copy(f.fileno(), os.fsencode(out_path), level, threads,
+                             2 if bgzf else (1 if fastq_encoder else 0), piece)
     if n < 0:
         raise RuntimeError(f"tb_gzip_copy failed ({n})")
     return int(n)

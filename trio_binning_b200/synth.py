@@ -145,6 +145,54 @@ def random_reads(n_reads: int, mean_len: int, k: int, keys_a: np.ndarray, keys_b
     return bases, offsets, hap
 
 
+def genome_kmer_set(genome: np.ndarray, k: int) -> np.ndarray:
+    """All k-mers of a genome (uint8 letters) as the classifier finds them: the LSB-first
+    encoding of each window or of its reverse complement, whichever is smaller (so every stored
+    k-mer is findable, quirk Q1), distinct and sorted."""
+    code = np.zeros(256, dtype=np.uint64)
+    for i, c in enumerate(b"ACGT"):
+        code[c] = i
+    c = code[genome]
+    n = len(c) - k + 1
+    fwd = np.zeros(n, dtype=np.uint64)
+    rc = np.zeros(n, dtype=np.uint64)
+    for j in range(k):
+        fwd |= c[j:j + n] << np.uint64(2 * j)
+        rc |= (np.uint64(3) - c[j:j + n]) << np.uint64(2 * (k - 1 - j))
+    return np.unique(np.minimum(fwd, rc))
+
+
+def mosaic_reads(n_reads: int, mean_len: int, k: int, genome_a: np.ndarray, genome_b: np.ndarray, seed: int,
+                 fraction: float, segment: int = 200):
+    """Reads whose windows hit a set at a chosen density: random sequence with `fraction` of each
+    read overwritten by `segment`-base pieces of its haplotype's genome (either strand).  With sets
+    from genome_kmer_set about fraction * (segment - k + 1) / segment of all windows are hits.
+    Returns (bases, offsets, hap) like random_reads."""
+    rng = np.random.default_rng(seed)
+    lens = read_lengths(n_reads, mean_len, rng, min_len=max(k + 1, segment + 1))
+    offsets = np.zeros(n_reads + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    total = int(offsets[-1])
+    bases = _LETTERS[rng.integers(0, 4, size=total, dtype=np.uint8)]
+    hap = rng.integers(0, 2, size=n_reads).astype(np.int8)
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[_LETTERS] = _LETTERS[::-1]
+    for h, genome in ((0, genome_a), (1, genome_b)):
+        reads_h = np.nonzero(hap == h)[0]
+        n_seg = rng.poisson(lens[reads_h] * fraction / segment)
+        read_of = np.repeat(reads_h, n_seg)
+        if len(read_of) == 0:
+            continue
+        pos = (rng.random(len(read_of)) * (lens[read_of] - segment)).astype(np.int64) + offsets[read_of]
+        src = rng.integers(0, len(genome) - segment, size=len(read_of))
+        idx_dst = pos[:, None] + np.arange(segment)[None, :]
+        piece = genome[src[:, None] + np.arange(segment)[None, :]]
+        flip = rng.random(len(read_of)) < 0.5
+        piece[flip] = comp[piece[flip][:, ::-1]]
+        bases[idx_dst.ravel()] = piece.ravel()
+    return bases, offsets, hap
+
+
 def total_windows(offsets: np.ndarray, k: int) -> int:
     lens = np.diff(offsets)
     return int(np.maximum(lens - k + 1, 0).sum())
