@@ -313,8 +313,9 @@ int64_t tb_counter_select_unique(tb_kmer_counter *a, tb_kmer_counter *b, uint32_
 int tb_classifier_mark(tb_classifier *c, int slot, int which);
 int tb_classifier_elapsed(tb_classifier *c, int slot_from, int which_from, int slot_to,
                           int which_to, float *ms);
-/* Re-run the device part (pack + classify + decide; no copies) of the batch last
- * submitted to `slot`, `iters` times, timed with CUDA events on the slot's
+/* Re-run the device part (no copies) of the batch last submitted to `slot` -- pack + index +
+ * classify + fix-up + decide for an ASCII batch, index + classify + fix-up + decide for a
+ * host-packed one -- `iters` times, timed with CUDA events on the slot's
  * stream.  Returns total milliseconds in *ms_total and the classify kernel's
  * share in *ms_classify (measured with its own event pair).  Used by bench.py
  * for the HBM-resident figure and the roofline. */

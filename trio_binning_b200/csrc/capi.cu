@@ -305,6 +305,8 @@ struct Slot {
     char *d_bin = nullptr;
     tb_batch_view view;
     bool has_batch = false;
+    bool packed_resident = false;  // the slot's last batch arrived host-packed (no ASCII on the device)
+    int64_t packed_n_dirty = 0, packed_n_ub = 0;
     uint64_t windows = 0;
     int32_t *h_ca = nullptr;  // where the last batch's count_A went (for stats)
     uint64_t fixup_reads = 0;
@@ -412,6 +414,31 @@ int enqueue_kernels(tb_classifier *c, Slot &s, cudaEvent_t before_classify, cuda
     if (after_classify) CK(cudaEventRecord(after_classify, s.stream));
     CK(tb_launch_fixup(s.view, c->k, A, B, s.stream));
     CK(tb_launch_finalize(s.view, c->scale_a, c->scale_b, s.stream));
+    return 0;
+}
+
+// the device part of a host-packed batch: index + scatter of the rare words, classify, fix-up, decide
+int enqueue_packed_kernels(tb_classifier *c, Slot &s, cudaEvent_t before_classify, cudaEvent_t after_classify)
+{
+    const tb_set_view A = view_of(c->A), B = view_of(c->B);
+    const tb_batch_view &v = s.view;
+    cudaStream_t st = s.stream;
+    CK(tb_launch_index_packed(v, s.d_dirty_idx, s.d_e_words, s.packed_n_dirty, s.d_ub_read, s.d_ub_skip,
+                              s.packed_n_ub, st));
+    if (before_classify) CK(cudaEventRecord(before_classify, st));
+    if (c->d_pair && c->d_filter && c->mini) {
+        tb_pair_view P = { c->d_pair, c->pair_buckets };
+        CK(tb_launch_classify_pair_mini(v, c->k, P, c->d_filter, (c->filter_word_mask >> 3) + 1, c->filter_bits, c->p2_width, st));
+    } else if (c->d_pair && c->d_filter) {
+        tb_pair_view P = { c->d_pair, c->pair_buckets };
+        CK(tb_launch_classify_pair(v, c->k, P, c->d_filter, c->filter_word_mask, c->filter_bits, st));
+    } else if (c->d_filter)
+        CK(tb_launch_classify_filtered(v, c->k, A, B, c->d_filter, c->filter_mask, st));
+    else
+        CK(tb_launch_classify(v, c->k, A, B, st));
+    if (after_classify) CK(cudaEventRecord(after_classify, st));
+    CK(tb_launch_fixup(v, c->k, A, B, st));
+    CK(tb_launch_finalize(v, c->scale_a, c->scale_b, st));
     return 0;
 }
 
@@ -837,6 +864,7 @@ int tb_classifier_submit(tb_classifier *c, int slot, const char *bases, const in
     s.windows = windows;
     s.h_ca = count_A;
     s.has_batch = true;
+    s.packed_resident = false;
     if (n_reads == 0) return 0;
     if (total) CK(cudaMemcpyAsync(s.d_ascii, bases, (size_t)total, cudaMemcpyHostToDevice, s.stream));
     CK(cudaMemcpyAsync(s.d_offsets, offsets, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, s.stream));
@@ -910,7 +938,7 @@ int tb_classifier_submit_packed(tb_classifier *c, int slot, const tb_packed_batc
     v.bin = bin ? s.d_bin : nullptr;
     s.windows = windows;
     s.h_ca = count_A;
-    s.has_batch = false;  // no ASCII on the device: rerun_resident needs an ASCII batch
+    s.has_batch = false;  // no ASCII on the device: rerun_resident replays the packed form
     if (n_reads == 0) return 0;
     cudaStream_t st = s.stream;
     CK(cudaMemcpyAsync(s.d_F, pb->F, (size_t)(pb->n_tiles + 1) * 32 * 8, cudaMemcpyHostToDevice, st));
@@ -926,21 +954,10 @@ int tb_classifier_submit_packed(tb_classifier *c, int slot, const tb_packed_batc
         CK(cudaMemcpyAsync(s.d_ub_off, pb->ub_off, (size_t)pb->n_ub * 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(s.d_ub_bytes, pb->ub_bytes, (size_t)pb->ub_bytes_used, cudaMemcpyHostToDevice, st));
     }
-    const tb_set_view A = view_of(c->A), B = view_of(c->B);
-    CK(tb_launch_index_packed(v, s.d_dirty_idx, s.d_e_words, pb->n_dirty, s.d_ub_read, s.d_ub_skip,
-                              pb->n_ub, st));
-    if (c->d_pair && c->d_filter && c->mini) {
-        tb_pair_view P = { c->d_pair, c->pair_buckets };
-        CK(tb_launch_classify_pair_mini(v, c->k, P, c->d_filter, (c->filter_word_mask >> 3) + 1, c->filter_bits, c->p2_width, st));
-    } else if (c->d_pair && c->d_filter) {
-        tb_pair_view P = { c->d_pair, c->pair_buckets };
-        CK(tb_launch_classify_pair(v, c->k, P, c->d_filter, c->filter_word_mask, c->filter_bits, st));
-    } else if (c->d_filter)
-        CK(tb_launch_classify_filtered(v, c->k, A, B, c->d_filter, c->filter_mask, st));
-    else
-        CK(tb_launch_classify(v, c->k, A, B, st));
-    CK(tb_launch_fixup(v, c->k, A, B, st));
-    CK(tb_launch_finalize(v, c->scale_a, c->scale_b, st));
+    s.packed_resident = true;
+    s.packed_n_dirty = pb->n_dirty;
+    s.packed_n_ub = pb->n_ub;
+    if (enqueue_packed_kernels(c, s, nullptr, nullptr)) return -1;
     CK(cudaMemcpyAsync(count_A, s.d_ca, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(count_B, s.d_cb, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st));
     if (score_A) CK(cudaMemcpyAsync(score_A, s.d_sa, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, st));
@@ -996,7 +1013,7 @@ int tb_classifier_rerun_resident_flush(tb_classifier *c, int slot, int iters, ui
     if (iters < 1 || iters > 4096) return fail("iters must be 1..4096");
     CK(cudaSetDevice(c->device));
     Slot &s = c->slots[(size_t)slot];
-    if (!s.has_batch || s.view.n_reads == 0) return fail("no batch resident in slot %d", slot);
+    if ((!s.has_batch && !s.packed_resident) || s.view.n_reads == 0) return fail("no batch resident in slot %d", slot);
     void *scratch = nullptr;
     DeviceScratch guard;
     if (flush_bytes) {
@@ -1012,7 +1029,9 @@ int tb_classifier_rerun_resident_flush(tb_classifier *c, int slot, int iters, ui
         // between timed steps: overwrite a buffer larger than L2 so nothing survives in cache
         if (scratch) CK(cudaMemsetAsync(scratch, i & 0xFF, flush_bytes, s.stream));
         CK(cudaEventRecord(ev[(size_t)4 * i], s.stream));
-        if (enqueue_kernels(c, s, ev[(size_t)4 * i + 1], ev[(size_t)4 * i + 2])) return -1;
+        if (s.packed_resident ? enqueue_packed_kernels(c, s, ev[(size_t)4 * i + 1], ev[(size_t)4 * i + 2])
+                              : enqueue_kernels(c, s, ev[(size_t)4 * i + 1], ev[(size_t)4 * i + 2]))
+            return -1;
         CK(cudaEventRecord(ev[(size_t)4 * i + 3], s.stream));
     }
     CK(cudaStreamSynchronize(s.stream));
@@ -1074,7 +1093,7 @@ int tb_classifier_stats(tb_classifier *c, int slot, uint64_t *n_windows, uint64_
     if (!c) return fail("null classifier");
     if (slot < 0 || slot >= (int)c->slots.size()) return fail("slot %d out of range", slot);
     Slot &s = c->slots[(size_t)slot];
-    if (!s.has_batch) return fail("no batch in slot %d", slot);
+    if (!s.has_batch && !s.packed_resident) return fail("no batch in slot %d", slot);
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(s.stream));
     uint64_t hits_a = 0;

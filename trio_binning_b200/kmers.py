@@ -203,6 +203,17 @@ lib.tb_set_clone.restype = HashSet
 lib.tb_route_fastx.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_int64, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int64, C.c_int,
                                C.POINTER(StreamStats)]
+lib.tb_counter_create.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int]
+lib.tb_counter_create.restype = C.c_void_p
+lib.tb_counter_destroy.argtypes = [C.c_void_p]
+lib.tb_counter_destroy.restype = None
+lib.tb_counter_add_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+lib.tb_counter_add_fastx.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+lib.tb_counter_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+lib.tb_counter_histogram.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+lib.tb_counter_select_unique.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                         C.c_void_p, C.c_uint64]
+lib.tb_counter_select_unique.restype = C.c_int64
 lib.tb_float_repr.argtypes = [C.c_double, C.c_char_p, C.c_int]
 lib.tb_fastx_dump.argtypes = [C.c_char_p, C.c_int]
 lib.tb_fastx_dump.restype = C.c_int64
@@ -726,6 +737,87 @@ def route_fastx_file(reads_path: str, bins: str, out_a: str, out_b: str, out_u: 
     if rc != 0:
         raise RuntimeError(f"tb_route_fastx failed ({rc}): {_error()}")
     return stats.as_dict()
+
+
+class KmerCounter:
+    """Canonical k-mer counting table on the GPU (tb_counter_* of the C ABI): what the reference's
+    find-unique-kmers gets from `kmc` (find_unique_kmers.py:62-103).  Keys are MSB-first 2-bit
+    encodings of the canonical k-mer (the lexicographically smaller strand)."""
+
+    COUNTER_MAX = 255  # KMC -cs default
+    DB_MIN = 2         # KMC -ci default: k-mers seen once are not in a database
+
+    def __init__(self, k: int, n_slots: int, part: int = 0, n_parts: int = 1, device: Optional[int] = None):
+        self.k = k
+        dev = lib.tb_get_device() if device is None else device
+        self._h = lib.tb_counter_create(k, int(n_slots), part, n_parts, dev)
+        if not self._h:
+            raise RuntimeError(f"KmerCounter: {_error()}")
+
+    def add_reads(self, reads: Sequence[str]) -> None:
+        bases, offsets = pack_reads(reads)
+        self.add_packed(bases, offsets)
+
+    def add_packed(self, bases: np.ndarray, offsets: np.ndarray) -> None:
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        _check(lib.tb_counter_add_batch(self._h, bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1))
+
+    def add_file(self, path: str, batch_bases: int = 64 << 20, threads: int = 0) -> Tuple[int, int]:
+        """Count every record of a FASTA/FASTQ(.gz) file (native reader); returns (reads, bases)."""
+        n_reads, n_bases = C.c_uint64(), C.c_uint64()
+        rc = lib.tb_counter_add_fastx(self._h, os.fsencode(path), batch_bases, threads, C.byref(n_reads), C.byref(n_bases))
+        if rc != 0:
+            raise RuntimeError(f"counting k-mers of {path} failed ({rc}): {_error()}")
+        return n_reads.value, n_bases.value
+
+    def stats(self) -> dict:
+        """Waits for the counting to finish; raises if the table filled up."""
+        w, d, s = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        rc = lib.tb_counter_stats(self._h, C.byref(w), C.byref(d), C.byref(s))
+        out = {"windows": w.value, "distinct": d.value, "slots": s.value}
+        if rc != 0:
+            raise OverflowError(_error())
+        return out
+
+    def histogram(self, n_bins: int = 256) -> np.ndarray:
+        """hist[i] = distinct k-mers seen i times; the last bin holds everything >= n_bins-1."""
+        hist = np.zeros(n_bins, dtype=np.uint64)
+        _check(lib.tb_counter_histogram(self._h, hist.ctypes.data, n_bins))
+        return hist
+
+    def select_unique(self, other: Optional["KmerCounter"], min_count: int, max_count: int) -> np.ndarray:
+        """Sorted keys of this database that are absent from `other`'s and whose saturated count is in
+        [min_count, max_count] (kmers_subtract + kmc_dump -ci -cx, find_unique_kmers.py:171-233)."""
+        oh = other._h if other is not None else None
+        n = lib.tb_counter_select_unique(self._h, oh, min_count, max_count, self.DB_MIN, self.COUNTER_MAX, None, 0)
+        if n < 0:
+            raise RuntimeError(_error())
+        out = np.zeros(int(n), dtype=np.uint64)
+        if n:
+            m = lib.tb_counter_select_unique(self._h, oh, min_count, max_count, self.DB_MIN, self.COUNTER_MAX,
+                                             out.ctypes.data, int(n))
+            if m != n:
+                raise RuntimeError(f"selection changed between two passes ({n} then {m}): {_error()}")
+        out.sort()
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            lib.tb_counter_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 def float_repr(x: float) -> str:
