@@ -515,7 +515,8 @@ def test_native_pipeline_equals_python_io(kmers, capsys, tmp_path):
     for plain in (False, True):
         outs = {}
         for mode, extra in (("native", []), ("python", ["--python-io"]), ("native_zlib", ["--no-fastq-gzip"]),
-                            ("native_1gpu", ["--gpus", "1"]), ("native_2gpu", ["--gpus", "2"])):
+                            ("native_1gpu", ["--gpus", "1"]), ("native_2gpu", ["--gpus", "2"]),
+                            ("native_3workers", ["--gpu-workers", "3"])):
             d = tmp_path / f"{mode}_{plain}"
             d.mkdir()
             argv = ["classify-by-kmers", str(reads), str(pa), str(pb), "--haplotype-a-out-prefix", str(d / "A"),

@@ -5,7 +5,6 @@ stage timings.  usage: cli_multi_gpu.py [N] [n_reads] [mean_len]"""
 import gzip
 import hashlib
 import os
-import random
 import subprocess
 import sys
 import tempfile
@@ -25,12 +24,15 @@ pa, pb = os.path.join(tmp, "hapA.txt"), os.path.join(tmp, "hapB.txt")
 synth.write_kmer_file(pa, ka, k)
 synth.write_kmer_file(pb, kb, k)
 bases, offsets, _ = synth.random_reads(n_reads, mean_len, k, ka, kb, seed=6, plant_every=500, invalid_rate=0.0005)
-rng = random.Random(1)
+import numpy as np  # noqa: E402
+
+qual_pool = np.random.default_rng(1).integers(33, 74, size=1 << 22, dtype=np.uint8)
 reads = os.path.join(tmp, "reads.fastq")
 with open(reads, "wb") as f:
     for r in range(len(offsets) - 1):
         s = bases[offsets[r]:offsets[r + 1]].tobytes()
-        q = bytes(rng.choices(range(33, 74), k=len(s))) if len(s) < 50_000 else b"I" * len(s)
+        start = (r * 7919) % (len(qual_pool) - len(s) - 1) if len(s) < len(qual_pool) - 1 else 0
+        q = qual_pool[start:start + len(s)].tobytes() if len(s) < len(qual_pool) - 1 else b"I" * len(s)
         f.write(b"@read%d extra\n" % r + s + b"\n+\n" + q + b"\n")
 
 

@@ -8,3 +8,4 @@ df -h /tmp | tail -1 > gpurun_out/r2_df.txt
 tail -3 gpurun_out/r2_sanitizer_memcheck.txt gpurun_out/r2_sanitizer_racecheck.txt
 timeout 1500 python bench.py --workload c2 --steps 10 --no-cpu-baseline --no-other-workloads --no-gather --pipeline-gbases 5 > gpurun_out/r2_pipeline_5gbases.json 2> gpurun_out/r2_pipeline_5gbases.err
 tail -3 gpurun_out/r2_pipeline_5gbases.err
+timeout 900 python bench.py > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err; tail -3 gpurun_out/r2_bench_n1.err

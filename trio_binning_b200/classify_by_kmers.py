@@ -46,6 +46,10 @@ _B200_ARGUMENTS = (
     (("--gpus",), dict(type=int, default=0,
                        help="number of GPUs to spread the batches over, 0 = all visible ones; the sets are "
                             "replicated on each, the output does not depend on it (B200 addition)")),
+    (("--gpu-workers",), dict(type=int, default=0,
+                              help="device worker threads of the pipeline, 0 = one per GPU used; more than that wrap "
+                                   "around the GPUs, each worker with its own replica of the sets (B200 addition; "
+                                   "exercises the multi-GPU merge on a single-GPU machine)")),
     (("--gzip-level",), dict(type=int, default=6,
                              help="zlib level for output chunks the FASTQ-aware encoder declines (short reads) "
                                   "or for everything with --no-fastq-gzip: 6 costs a fraction of the time of 9, "
@@ -106,6 +110,8 @@ def _main_native(args):
     n_gpus = kmers.device_count() if args.gpus <= 0 else min(args.gpus, kmers.device_count())
     first = kmers.lib.tb_get_device()
     devices = [first] + [d for d in range(kmers.device_count()) if d != first][: n_gpus - 1]
+    if args.gpu_workers > len(devices):
+        devices = [devices[i % len(devices)] for i in range(args.gpu_workers)]
     sets_a = [args.haplotype_a_kmers] + [kmers.clone_kmer_hash_set(args.haplotype_a_kmers, d) for d in devices[1:]]
     sets_b = [args.haplotype_b_kmers] + [kmers.clone_kmer_hash_set(args.haplotype_b_kmers, d) for d in devices[1:]]
     sys.stdout.flush()

@@ -454,7 +454,10 @@ int build_filter(tb_classifier *c)
     // minimizer-addressed sectors (default whenever the pair table exists): consecutive windows
     // share bitmap sectors, so the bitmap may be far larger than L2 and still cheap to read
     c->mini = pair_ok && env_int("TB_MINIMIZER", 1) != 0;
-    c->p2_width = env_int("TB_P2_WIDTH", 0) >= 4 ? 4 : 2;
+    {
+        const int w = env_int("TB_P2_WIDTH", 0);
+        c->p2_width = w >= 4 ? 4 : (w == 1 ? 1 : 2);  // 1 = warp-cooperative phase 2
+    }
     if (m < 0) {
         const uint64_t n = c->A->n_distinct + c->B->n_distinct;
         if (c->mini) {

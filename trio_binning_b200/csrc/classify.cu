@@ -930,28 +930,91 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
         if (lane == 0 && np) atomicAdd(b.n_pass, (unsigned long long)np);
     }
 
-    // ---- phase 2 (as in k_classify_pair).  P2 survivors per lane and round: the whole warp pays
-    // for every slot, so the launcher picks 2 where ~1% of the windows pass (most lanes hold none
-    // or one) and 4 where more do
     uint32_t hit_a = 0, hit_b = 0;
     uint32_t mm = pass;
-    while (mm) {
-        int j[P2];
-        uint64_t key[P2];
-        uint32_t bkt[P2];
-        tb_bucket bk[P2];
+    if (P2 == 0) {
+        // ---- phase 2, warp-cooperative: the warp's survivors go through a queue in shared memory
+        // so that the table probes -- the part that waits for HBM -- are spread evenly over the
+        // lanes whatever lane the survivors came from.  With reads that carry real haplotype
+        // k-mers a few per cent of all windows survive and they cluster (a heterozygous site makes
+        // k consecutive windows hit): lane by lane the warp would run as many rounds as its
+        // unluckiest lane needs.  Fill: every lane that has survivors left pushes one key per step,
+        // four steps (128 entries at most) per batch.  Probe: entry e is handled by lane e mod 32,
+        // two loads in flight.  Read back: every lane collects the tags of what it pushed.
+        __shared__ unsigned long long q_key[4][128];
+        __shared__ unsigned char q_tag[4][128];
+        const int wi = threadIdx.x >> 5;
+        const unsigned lt = (1u << lane) - 1u;
+        while (__any_sync(0xFFFFFFFFu, mm != 0)) {
+            uint32_t pos_pack = 0, j_pack = 0;
+            int cnt = 0, n = 0;
 #pragma unroll
-        for (int q = 0; q < P2; q++) {
+            for (int step = 0; step < 4; step++) {
+                const bool have = mm != 0;
+                const unsigned b = __ballot_sync(0xFFFFFFFFu, have);
+                if (have) {
+                    const int j = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const int pos = n + __popc(b & lt);
+                    q_key[wi][pos] = window_key<0>(c, j, k, kmask);
+                    pos_pack |= (uint32_t)pos << (8 * cnt);
+                    j_pack |= (uint32_t)j << (5 * cnt);
+                    cnt++;
+                }
+                n += __popc(b);
+            }
+            __syncwarp();
+            for (int base = 0; base < n; base += 64) {
+                const int e0 = base + lane, e1 = base + 32 + lane;
+                const bool v0 = e0 < n, v1 = e1 < n;
+                const uint64_t key0 = v0 ? q_key[wi][e0] : 0, key1 = v1 ? q_key[wi][e1] : 0;
+                const uint32_t bkt0 = tb_pair_bucket_of(tb_hash64(key0), P.n_buckets);
+                const uint32_t bkt1 = tb_pair_bucket_of(tb_hash64(key1), P.n_buckets);
+                tb_bucket bk0, bk1;
+                if (v0) bk0 = tb_load_bucket(P.table + bkt0);
+                if (v1) bk1 = tb_load_bucket(P.table + bkt1);
+                if (v0) {
+                    uint32_t tags = tb_pair_tags(bk0, key0);
+                    if (!tags && tb_pair_bucket_full(bk0)) tags = tb_pair_overflow(P, key0, bkt0);
+                    q_tag[wi][e0] = (unsigned char)tags;
+                }
+                if (v1) {
+                    uint32_t tags = tb_pair_tags(bk1, key1);
+                    if (!tags && tb_pair_bucket_full(bk1)) tags = tb_pair_overflow(P, key1, bkt1);
+                    q_tag[wi][e1] = (unsigned char)tags;
+                }
+            }
+            __syncwarp();
+            for (int q = 0; q < cnt; q++) {
+                const uint32_t tags = q_tag[wi][(pos_pack >> (8 * q)) & 0xFFu];
+                const int j = (j_pack >> (5 * q)) & 31;
+                hit_a |= (tags & 1u) << j;
+                hit_b |= ((tags == 2u) ? 1u : 0u) << j;
+            }
+            __syncwarp();
+        }
+    }
+    // ---- phase 2, lane by lane (as in k_classify_pair).  P2 survivors per lane and round: the
+    // whole warp pays for every slot, so 2 where ~1% of the windows pass (most lanes hold none or
+    // one) and 4 where more do
+    while (P2 != 0 && mm) {
+        constexpr int PW = P2 ? P2 : 1;
+        int j[PW];
+        uint64_t key[PW];
+        uint32_t bkt[PW];
+        tb_bucket bk[PW];
+#pragma unroll
+        for (int q = 0; q < PW; q++) {
             j[q] = mm ? __ffs(mm) - 1 : -1;
             if (mm) mm &= mm - 1;
             key[q] = window_key<0>(c, j[q] < 0 ? 0 : j[q], k, kmask);
             bkt[q] = tb_pair_bucket_of(tb_hash64(key[q]), P.n_buckets);
         }
 #pragma unroll
-        for (int q = 0; q < P2; q++)
+        for (int q = 0; q < PW; q++)
             if (j[q] >= 0) bk[q] = tb_load_bucket(P.table + bkt[q]);
 #pragma unroll
-        for (int q = 0; q < P2; q++) {
+        for (int q = 0; q < PW; q++) {
             if (j[q] < 0) continue;
             uint32_t tags = tb_pair_tags(bk[q], key[q]);
             if (!tags && tb_pair_bucket_full(bk[q])) tags = tb_pair_overflow(P, key[q], bkt[q]);
@@ -1131,6 +1194,8 @@ cudaError_t launch_pair_mini_k(const tb_batch_view &b, int k, tb_pair_view P, co
     if (n_bits == 2) {
         if (p2_width >= 4)
             k_classify_pair_mini<K, 8, 2, 4><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors);
+        else if (p2_width == 1 && tpb == 128)  // warp-cooperative phase 2 (its queue is sized for 4 warps)
+            k_classify_pair_mini<K, 8, 2, 0><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors);
         else
             k_classify_pair_mini<K, 8, 2, 2><<<blocks, tpb, 0, stream>>>(b, k, P, filter, n_sectors);
     } else {

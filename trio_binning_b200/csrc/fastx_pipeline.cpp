@@ -91,13 +91,20 @@ public:
         for (auto &w : workers_) w.join();
         if (fd_ >= 0) ::close(fd_);
     }
-    // Next line into `line` INCLUDING its terminator translated to '\n' (absent only at
-    // end of input).  Returns false at end of input (or on a read error: see error()).
-    bool next(std::string &line)
+    // Next line INCLUDING its terminator translated to '\n' (absent only at end of input), as a
+    // view: *data points into the current chunk when the whole line lies inside it (the common
+    // case: no copy), else into a spill buffer that collects the pieces.  The view stays valid
+    // until the next call.  Returns false at end of input (or on a read error: see error()).
+    bool next(const char *&data, size_t &len)
     {
-        line.clear();
+        bool spilled = false;
         for (;;) {
-            if (pos_ == len_ && !fill()) return !line.empty();
+            if (pos_ == len_ && !fill()) {
+                if (!spilled || spill_.empty()) return false;
+                data = spill_.data();
+                len = spill_.size();
+                return true;
+            }
             if (pending_cr_) {
                 // a '\r' ended the previous line; swallow the '\n' of a "\r\n" pair
                 pending_cr_ = false;
@@ -106,20 +113,35 @@ public:
                     continue;
                 }
             }
-            const char *p = cur_ + pos_;
+            char *p = cur_ + pos_;
             const size_t avail = len_ - pos_;
             // first '\n' or '\r' (two vectorised scans; '\r' is looked for only up to the '\n')
             const char *nl = (const char *)memchr(p, '\n', avail);
             size_t i = nl ? (size_t)(nl - p) : avail;
             if (const char *cr = (const char *)memchr(p, '\r', i)) i = (size_t)(cr - p);
-            line.append(p, i);
             pos_ += i;
             if (i < avail) {
-                if (p[i] == '\r') pending_cr_ = true;
+                if (p[i] == '\r') {
+                    pending_cr_ = true;
+                    p[i] = '\n';  // the chunk is ours: translate in place
+                }
                 pos_++;
-                line.push_back('\n');
+                if (!spilled) {
+                    data = p;
+                    len = i + 1;
+                } else {
+                    spill_.append(p, i + 1);
+                    data = spill_.data();
+                    len = spill_.size();
+                }
                 return true;
             }
+            // the line runs past this chunk: collect its pieces
+            if (!spilled) {
+                spill_.clear();
+                spilled = true;
+            }
+            spill_.append(p, i);
         }
     }
     uint64_t bytes_in() const { return bytes_in_; }
@@ -403,7 +425,8 @@ private:
     std::vector<ChunkPtr> free_;
     size_t max_in_flight_ = 3;
     ChunkPtr cur_chunk_;
-    const char *cur_ = nullptr;
+    std::string spill_;  // a line that straddles chunks
+    char *cur_ = nullptr;
     size_t pos_ = 0, len_ = 0;
     uint64_t bytes_in_ = 0, bgzf_bytes_ = 0;
     std::atomic<uint64_t> inflate_ns_{ 0 };
@@ -419,9 +442,8 @@ inline size_t n_chars(const char *p, size_t n)
 }
 
 // Python's line[:-1]: drop the last CHARACTER whatever it is
-inline size_t chop_len(const std::string &line)
+inline size_t chop_len(const char *line, size_t n)
 {
-    size_t n = line.size();
     if (n == 0) return 0;
     n--;
     while (n > 0 && ((unsigned char)line[n] & 0xC0) == 0x80) n--;
@@ -564,19 +586,20 @@ struct Reader {
         int64_t seq_start = 0;  // where the current record's sequence starts in cur->bases
         int64_t fill = 0;       // bytes of cur->bases in use (incl. the record being read)
 
-        std::string line, header;
+        const char *lp = nullptr;  // the current line (view, valid until the next src.next)
+        size_t ln = 0;
+        std::string header;
         bool have_header = false;  // a pending header line (already chopped, non-empty)
         bool ok = true;
-        auto emit = [&](const std::string &name, int64_t seq_len, bool has_qual, const std::string &qual) {
-            // close the batch first if this record would overflow a non-empty batch
+        // append a record whose name (and, for FASTQ, quality) already sit in cur->text
+        auto emit = [&](uint64_t name_off, uint32_t name_len, int64_t seq_len, bool has_qual, uint64_t qual_off,
+                        uint32_t qual_len) {
             Rec r;
-            r.name_off = cur->text.size();
-            r.name_len = (uint32_t)name.size();
-            cur->text.append(name);
-            r.qual_off = cur->text.size();
-            r.qual_len = (uint32_t)qual.size();
+            r.name_off = name_off;
+            r.name_len = name_len;
+            r.qual_off = qual_off;
+            r.qual_len = qual_len;
             r.has_qual = has_qual;
-            cur->text.append(qual);
             cur->recs.push_back(r);
             cur->offsets.push_back(seq_start + seq_len);
             n_reads++;
@@ -589,14 +612,13 @@ struct Reader {
                 fill = 0;
             }
         };
-        std::string name, qual;
         while (ok) {
             // ---- find the next header unless one is pending
             if (!have_header) {
                 bool found = false;
-                while (src.next(line)) {
-                    if (line[0] == '>' || line[0] == '@') {
-                        header.assign(line, 0, chop_len(line));
+                while (src.next(lp, ln)) {
+                    if (lp[0] == '>' || lp[0] == '@') {
+                        header.assign(lp, chop_len(lp, ln));
                         found = true;
                         break;
                     }
@@ -604,25 +626,27 @@ struct Reader {
                 if (!found || header.empty()) break;
             }
             have_header = false;
+            const uint64_t name_off = cur->text.size();
             {
                 const size_t sp = header.find(' ', 1);
-                name.assign(header, 1, sp == std::string::npos ? std::string::npos : sp - 1);
+                cur->text.append(header, 1, sp == std::string::npos ? std::string::npos : sp - 1);
             }
+            const uint32_t name_len = (uint32_t)(cur->text.size() - name_off);
             // ---- sequence lines until a line starting with '@', '+' or '>'
             seq_start = fill = cur->total();
             bool got_marker = false;
-            while (src.next(line)) {
-                const char c = line[0];
+            while (src.next(lp, ln)) {
+                const char c = lp[0];
                 if (c == '@' || c == '+' || c == '>') {
-                    header.assign(line, 0, chop_len(line));
+                    header.assign(lp, chop_len(lp, ln));
                     got_marker = true;
                     break;
                 }
-                const size_t n = chop_len(line);
+                const size_t n = chop_len(lp, ln);
                 if (fill + (int64_t)n > cur->cap_bases) {
-                    if (!cur->grow_bases(fill + (int64_t)n, fill)) { error = "pinned allocation failed"; ok = false; break; }
+                    if (!cur->grow_bases(fill + (int64_t)n, fill)) { error = "allocation of a batch failed"; ok = false; break; }
                 }
-                memcpy(cur->bases + fill, line.data(), n);
+                memcpy(cur->bases + fill, lp, n);
                 fill += (int64_t)n;
             }
             if (!ok) break;
@@ -630,30 +654,32 @@ struct Reader {
             const bool pending = got_marker && !header.empty();
             if (!pending || header[0] != '+') {
                 // FASTA record (or end of input)
-                emit(name, seq_len, false, std::string());
+                emit(name_off, name_len, seq_len, false, cur->text.size(), 0);
                 if (!pending) break;
                 have_header = true;
                 continue;
             }
-            // ---- FASTQ: quality lines until at least len(seq) CHARACTERS were read
+            // ---- FASTQ: quality lines, straight into the batch's text, until at least len(seq)
+            // ---- CHARACTERS were read
             const size_t seq_chars = n_chars(cur->bases + seq_start, (size_t)seq_len);
-            qual.clear();
+            const uint64_t qual_off = cur->text.size();
             size_t have = 0;
             bool complete = false;
-            while (src.next(line)) {
-                const size_t n = chop_len(line);
-                qual.append(line, 0, n);
-                have += n_chars(line.data(), line.size()) - 1;
+            while (src.next(lp, ln)) {
+                const size_t n = chop_len(lp, ln);
+                cur->text.append(lp, n);
+                have += n_chars(lp, ln) - 1;
                 if (have >= seq_chars) {
                     complete = true;
                     break;
                 }
             }
             if (complete) {
-                emit(name, seq_len, true, qual);
+                emit(name_off, name_len, seq_len, true, qual_off, (uint32_t)(cur->text.size() - qual_off));
             } else {
                 // input ended inside the quality block: record without qualities, then stop
-                emit(name, seq_len, false, std::string());
+                // (the partial quality text stays behind in the batch, unreferenced)
+                emit(name_off, name_len, seq_len, false, cur->text.size(), 0);
                 break;
             }
         }
