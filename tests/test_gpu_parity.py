@@ -785,3 +785,55 @@ def test_canonical_orientation_sets(kmers, oracle):
     oracle.set_free(ob)
     kmers.destroy_kmer_hash_set(A)
     kmers.destroy_kmer_hash_set(B)
+
+
+def test_long_runs_of_non_acgt(kmers, oracle):
+    """gap-filled / assembly-like input.  Runs of N from 1 kb to 400 kb -- inside reads,
+    at their start (the Q3-UB fix-up path), at their end, spanning many tiles, whole reads of N --
+    must stay exact on both routes (device pack and host pack), and must not take forever."""
+    import time
+
+    from trio_binning_b200 import synth
+
+    k = 21
+    ka, kb = synth.random_kmer_sets(50_000, 50_000, k, seed=41)
+    ka = np.concatenate([ka, np.zeros(1, dtype=np.uint64)])  # key 0 (poly-A) is what an all-N window looks up
+    rng = np.random.default_rng(42)
+    bases, offsets, _ = synth.random_reads(40, 600_000, k, ka, kb, seed=43, plant_every=300)
+    bases = bases.copy()
+    n = len(offsets) - 1
+    for r in range(n):
+        s, e = int(offsets[r]), int(offsets[r + 1])
+        length = int(rng.choice([1_000, 30_000, 200_000, 400_000]))
+        length = min(length, e - s)
+        where = r % 4
+        a = s if where == 0 else (e - length if where == 1 else s + int(rng.integers(0, e - s - length + 1)))
+        if where == 3:
+            a, length = s, e - s  # the whole read
+        bases[a:a + length] = ord("N")
+        if r % 5 == 0:  # a second, short run and a lone lowercase base
+            b2 = s + int(rng.integers(0, e - s - 50))
+            bases[b2:b2 + 37] = ord("n")
+    A, B = kmers.create_kmer_hash_set_from_ints(ka, k), kmers.create_kmer_hash_set_from_ints(kb, k)
+    oa, ob = _oracle_sets(oracle, ka, kb, k)
+    t0 = time.time()
+    ca, cb, *_ = kmers.classify_packed(bases, offsets, A, B)
+    t_gpu = time.time() - t0
+    wa, wb = oracle.count_batch_threads(bases, offsets, oa, ob)
+    bad = np.nonzero((ca != wa) | (cb != wb))[0]
+    assert bad.size == 0, (bad[:5], ca[bad[:5]], wa[bad[:5]], cb[bad[:5]], wb[bad[:5]])
+    assert wa.sum() > 100_000  # the all-N windows hit key 0 in set A by the thousand
+    total = int(offsets[-1])
+    with kmers.Classifier(A, B, total * 12, n, 1) as clf:
+        # room for the Q3-UB prefixes the host packer ships for reads that start with a run (the
+        # pipeline sends such a batch as ASCII when they do not fit: tb_pack_reads returns -3)
+        pb = kmers.PackedBatch(total * 12, n)
+        pb.pack(bases, offsets, k)
+        clf.submit_packed(0, pb)
+        pa, pbb, *_ = clf.result(0)
+        assert (pa == wa).all() and (pbb == wb).all()
+    assert t_gpu < 20, f"{t_gpu:.1f} s for {total} bases"
+    oracle.set_free(oa)
+    oracle.set_free(ob)
+    kmers.destroy_kmer_hash_set(A)
+    kmers.destroy_kmer_hash_set(B)

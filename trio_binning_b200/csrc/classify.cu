@@ -58,25 +58,33 @@ __device__ __forceinline__ int64_t read_of_position(const int64_t *__restrict__ 
     return lo;
 }
 
-// code of the nearest valid base strictly before flat position x (0 if none)
-__device__ __noinline__ uint32_t lookback_code(const unsigned char *__restrict__ ascii, int64_t x)
+// Code of the nearest valid base strictly before flat position x0 (0 if none), found by a whole
+// warp: x0 is a multiple of 1024, the start of the warp's tile.  Every lane inspects its own 16 bytes of the 512 before
+// the current position, so a run of L non-ACGT bases costs L/512 steps per TILE that lies in it
+// instead of L/16 steps per WORD (gap-filled, assembly-like inputs).
+__device__ __noinline__ uint32_t warp_lookback_code(const unsigned char *__restrict__ ascii, int64_t x0, int lane)
 {
-    int64_t p = x - 1;
-    // byte-wise down to a 16-byte boundary, then 16 bytes at a time
-    while (p >= 0 && ((p + 1) & 15)) {
-        unsigned char c = ascii[p];
-        if (tb_base_valid(c)) return tb_base_code(c);
-        p--;
-    }
-    while (p >= 15) {
-        uint4 q = *reinterpret_cast<const uint4 *>(ascii + p - 15);
-        if (valid_mask4(q.x) | valid_mask4(q.y) | valid_mask4(q.z) | valid_mask4(q.w)) break;
-        p -= 16;
-    }
-    while (p >= 0) {
-        unsigned char c = ascii[p];
-        if (tb_base_valid(c)) return tb_base_code(c);
-        p--;
+    for (int64_t base = x0; base > 0; base -= 512) {
+        const int64_t p = base - 16 * (int64_t)(lane + 1);  // lane 0 holds the nearest 16 bytes
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (p >= 0) q = *reinterpret_cast<const uint4 *>(ascii + p);
+        const bool any = (valid_mask4(q.x) | valid_mask4(q.y) | valid_mask4(q.z) | valid_mask4(q.w)) != 0;
+        const unsigned am = __ballot_sync(0xFFFFFFFFu, any);
+        if (am) {
+            const int nearest = __ffs(am) - 1;
+            uint32_t code = 0;
+            if (lane == nearest) {
+                const uint32_t words[4] = { q.x, q.y, q.z, q.w };
+                for (int i = 15; i >= 0; i--) {
+                    const unsigned char c = (unsigned char)(words[i >> 2] >> (8 * (i & 3)));
+                    if (tb_base_valid(c)) {
+                        code = tb_base_code(c);
+                        break;
+                    }
+                }
+            }
+            return __shfl_sync(0xFFFFFFFFu, code, nearest);
+        }
     }
     return 0;
 }
@@ -141,9 +149,25 @@ k_pack(tb_batch_view b, int k)
         return;
     }
     const bool is_dirty = vmask != 0xFFFFFFFFu;
+    const unsigned dmask = __ballot_sync(0xFFFFFFFFu, is_dirty);
+    uint32_t carry = 0;
+    if (dmask) {
+        // rare path, warp-uniform part: what a dirty word inherits from before its first base.  A
+        // warp covers one tile (32 words), so the nearest valid base is either in a lower lane's
+        // word (one shuffle) or before the tile (one look-back for the whole warp).
+        const int lane = threadIdx.x & 31;
+        const bool has = vmask != 0;
+        const uint32_t last_code = has ? (uint32_t)(f >> (2 * (31 - __clz(vmask)))) & 3u : 0u;
+        const unsigned hmask = __ballot_sync(0xFFFFFFFFu, has);
+        const unsigned lower = hmask & ((1u << lane) - 1u);
+        const int src = lower ? 31 - __clz(lower) : -1;
+        const uint32_t from_lane = __shfl_sync(0xFFFFFFFFu, last_code, src < 0 ? 0 : src);
+        uint32_t tile_carry = 0;
+        if (__ballot_sync(0xFFFFFFFFu, is_dirty && src < 0)) tile_carry = warp_lookback_code(b.ascii, (w - lane) * 32, lane);
+        carry = src >= 0 ? from_lane : tile_carry;
+    }
     if (is_dirty) {
         // rare path: fill-forward stream + Q3-UB flagging
-        uint32_t carry = lookback_code(b.ascii, p0);
         uint64_t e = 0;
         int64_t r = -1, r_end = -1, r_start = 0;
         for (int i = 0; i < 32; i++) {
@@ -162,8 +186,7 @@ k_pack(tb_batch_view b, int k)
         }
         b.E[w] = e;
     }
-    unsigned d = __ballot_sync(0xFFFFFFFFu, is_dirty);
-    if ((threadIdx.x & 31) == 0) b.dirty[w >> 5] = d;
+    if ((threadIdx.x & 31) == 0) b.dirty[w >> 5] = dmask;
 }
 
 // ============================================================================
@@ -1096,7 +1119,22 @@ k_fixup(tb_batch_view b, int k, tb_set_view A, tb_set_view B)
         const uint32_t skip = b.skip[r];
         uint64_t rc = 0;  // sticky digits, slot s at bits 2s, zero-initialised
         int ca = 0, cb = 0;
-        for (uint32_t win = 0; win < skip; win++) {
+        // A read that STARTS with a long run of non-ACGT bytes: every window that lies entirely
+        // inside the run has forward digits 0 and a reverse-complement buffer nobody has written
+        // yet, i.e. key 0 -- one lookup for all of them instead of k byte tests per window.
+        uint32_t first = 0;
+        {
+            uint32_t run = 0;
+            while (run < skip + (uint32_t)k - 1u && !tb_base_valid(read[run])) run++;
+            if (run >= (uint32_t)k) {
+                first = run - (uint32_t)k + 1u < skip ? run - (uint32_t)k + 1u : skip;
+                if (tb_contains(A, 0))
+                    ca += (int)first;
+                else if (tb_contains(B, 0))
+                    cb += (int)first;
+            }
+        }
+        for (uint32_t win = first; win < skip; win++) {
             uint64_t fwd = 0;
             for (int j = 0; j < k; j++) {
                 unsigned char c = read[win + j];
