@@ -1138,10 +1138,13 @@ public:
         q_.pop_front();
         return v;
     }
-    size_t size()
+    bool try_pop(T &v)
     {
         std::lock_guard<std::mutex> lk(m_);
-        return q_.size();
+        if (q_.empty()) return false;
+        v = q_.front();
+        q_.pop_front();
+        return true;
     }
 
 private:
@@ -1305,7 +1308,19 @@ int run_pipeline(const PipelineConfig &cfg, tb_stream_stats *stats)
             done_q.push(p);
         };
         for (;;) {
-            PipeBatch *p = in.pop();
+            // A worker never sits on finished work: with nothing new to submit it completes what it
+            // has in flight and hands it to the router, then blocks.  (Holding batches while waiting
+            // for input starves the reader of free batches: the router cannot release later batches
+            // before the held one, and the pool runs dry.)
+            PipeBatch *p = nullptr;
+            if (!in.try_pop(p)) {
+                if (!inflight.empty()) {
+                    complete(inflight.front());
+                    inflight.pop_front();
+                    continue;
+                }
+                p = in.pop();
+            }
             if (!p) break;
             Batch &b = p->b;
             if (cfg.stub_bins) {
