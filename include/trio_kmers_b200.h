@@ -338,7 +338,10 @@ int tb_classifier_filter_info(tb_classifier *c, int *log2_bits, float *build_ms)
 /* The classifier's pair table (one tagged table for both sets, k <= 31; TB_PAIR=0 turns it
  * off): buckets (0 = none), distinct keys of A u B, bitmap bits set per key. */
 int tb_classifier_pair_info(tb_classifier *c, uint32_t *n_buckets, uint64_t *n_distinct, int *filter_bits);
-/* 1 if the classifier's bitmap sectors are addressed by the keys' minimizers, so that
+/* 2 if, in addition to the following, the bitmap's 128-byte lines are addressed by a coarser
+ * (13-mer) minimizer -- an experiment for bitmaps far beyond L2 at k = 20..24, enabled with
+ * TB_HIER=1 (measured slower than the default).
+ * 1 if the classifier's bitmap sectors are addressed by the keys' minimizers, so that
  * consecutive windows of a read re-use sectors from L1 (default whenever the pair table
  * exists, i.e. k <= 31; TB_MINIMIZER=0 selects hash-addressed words). */
 int tb_classifier_minimizer_mode(tb_classifier *c);

@@ -837,3 +837,50 @@ def test_long_runs_of_non_acgt(kmers, oracle):
     oracle.set_free(ob)
     kmers.destroy_kmer_hash_set(A)
     kmers.destroy_kmer_hash_set(B)
+
+
+@pytest.mark.parametrize("k", [20, 21, 22, 23, 24])
+def test_two_level_bitmap_addressing(kmers, oracle, k):
+    """The two-level addressing experiment (TB_HIER=1): bitmaps of >= 2^31 bits at
+    k = 20..24 address their 128-byte lines by a second, coarser minimizer.  Forced here on small sets
+    with TB_FILTER_LOG2=31.  Clean reads take the unrolled path, reads with non-ACGT bytes the general
+    one; both must agree with the oracle, and with the one-level result."""
+    from trio_binning_b200 import synth
+
+    ka, kb = synth.random_kmer_sets(300_000, 200_000, k, seed=300 + k)
+    A, B = kmers.create_kmer_hash_set_from_ints(ka, k), kmers.create_kmer_hash_set_from_ints(kb, k)
+    oa, ob = _oracle_sets(oracle, ka, kb, k)
+    batches = [synth.random_reads(300, 6000, k, ka, kb, seed=k, plant_every=150)[:2],
+               synth.random_reads(300, 5000, k, ka, kb, seed=k + 1, plant_every=150, invalid_rate=0.01)[:2],
+               synth.random_reads(20_000, 150, k, ka, kb, seed=k + 2, plant_every=80, fixed_len=True)[:2]]
+    results = {}
+    saved = {name: os.environ.get(name) for name in ("TB_FILTER_LOG2", "TB_HIER")}
+    try:
+        for hier in ("1", "0"):
+            os.environ["TB_FILTER_LOG2"] = "31"
+            os.environ["TB_HIER"] = hier
+            total = max(int(o[-1]) for _, o in batches)
+            with kmers.Classifier(A, B, total, 20_000, 1) as clf:
+                info = clf.filter_info()
+                assert info["log2_bits"] == 31 and info["two_level"] == (hier == "1")
+                for i, (bases, offsets) in enumerate(batches):
+                    clf.submit(0, bases, offsets)
+                    ca, cb, *_ = clf.result(0)
+                    results[(hier, i)] = (ca.copy(), cb.copy())
+                    assert clf.sector_runs(0) > 0
+    finally:
+        for name, value in saved.items():
+            if value is None:
+                os.environ.pop(name, None)
+            else:
+                os.environ[name] = value
+    for i, (bases, offsets) in enumerate(batches):
+        wa, wb = oracle.count_batch(bases, offsets, oa, ob)
+        for hier in ("1", "0"):
+            ca, cb = results[(hier, i)]
+            assert (ca == wa).all() and (cb == wb).all(), (k, hier, i)
+        assert wa.sum() > 0 and wb.sum() > 0
+    oracle.set_free(oa)
+    oracle.set_free(ob)
+    kmers.destroy_kmer_hash_set(A)
+    kmers.destroy_kmer_hash_set(B)

@@ -333,6 +333,7 @@ struct tb_classifier {
     int filter_bits = 1;
     uint32_t filter_word_mask = 0;  // (bits / 32) - 1
     bool mini = false;              // bitmap sectors addressed by the key's minimizer
+    int hier = 0;                   // ... and its 128-byte lines by a coarser (13-mer) minimizer
     int p2_width = 2;               // table probes per lane and phase-2 round (minimizer kernel)
 };
 
@@ -403,7 +404,7 @@ int enqueue_kernels(tb_classifier *c, Slot &s, cudaEvent_t before_classify, cuda
     if (before_classify) CK(cudaEventRecord(before_classify, s.stream));
     if (c->d_pair && c->d_filter && c->mini) {
         tb_pair_view P = { c->d_pair, c->pair_buckets };
-        CK(tb_launch_classify_pair_mini(s.view, c->k, P, c->d_filter, (c->filter_word_mask >> 3) + 1, c->filter_bits, c->p2_width, s.stream));
+        CK(tb_launch_classify_pair_mini(s.view, c->k, P, c->d_filter, (c->filter_word_mask >> 3) + 1, c->filter_bits, c->p2_width, c->hier, s.stream));
     } else if (c->d_pair && c->d_filter) {
         tb_pair_view P = { c->d_pair, c->pair_buckets };
         CK(tb_launch_classify_pair(s.view, c->k, P, c->d_filter, c->filter_word_mask, c->filter_bits, s.stream));
@@ -428,7 +429,7 @@ int enqueue_packed_kernels(tb_classifier *c, Slot &s, cudaEvent_t before_classif
     if (before_classify) CK(cudaEventRecord(before_classify, st));
     if (c->d_pair && c->d_filter && c->mini) {
         tb_pair_view P = { c->d_pair, c->pair_buckets };
-        CK(tb_launch_classify_pair_mini(v, c->k, P, c->d_filter, (c->filter_word_mask >> 3) + 1, c->filter_bits, c->p2_width, st));
+        CK(tb_launch_classify_pair_mini(v, c->k, P, c->d_filter, (c->filter_word_mask >> 3) + 1, c->filter_bits, c->p2_width, c->hier, st));
     } else if (c->d_pair && c->d_filter) {
         tb_pair_view P = { c->d_pair, c->pair_buckets };
         CK(tb_launch_classify_pair(v, c->k, P, c->d_filter, c->filter_word_mask, c->filter_bits, st));
@@ -504,9 +505,15 @@ int build_filter(tb_classifier *c)
         int nbits = env_int("TB_FILTER_BITS", 0);
         if (nbits != 1 && nbits != 2) nbits = ((double)n / (double)bits < 0.4) ? 2 : 1;
         c->filter_bits = nbits;
+        // two-level addressing (TB_HIER=1; off by default): where the bitmap is far beyond L2 (>= 2^31
+        // bits = 256 MB) and the k-mer has more 13-mers than m-mers (k = 20 .. 24).  Measured at C3 /
+        // C5: 18 % fewer DRAM bytes, but 35 % more L1 misses and 27 % / 8-24 % MORE time
+        // (profiles/r2_variants_hier.txt) -- kept as an experiment, not as the default
+        c->hier = (c->mini && nbits == 2 && c->p2_width == 2 && c->k >= 20 && c->k <= 24 && m >= 31 &&
+                   env_int("TB_HIER", 0) != 0) ? 1 : 0;
         if (c->mini)
             CK(tb_launch_pair_filter_build_mini(reinterpret_cast<const uint64_t *>(c->d_pair), nb * TB_SLOTS,
-                                                c->d_filter, (c->filter_word_mask >> 3) + 1, nbits, c->k, 0));
+                                                c->d_filter, (c->filter_word_mask >> 3) + 1, nbits, c->k, c->hier, 0));
         else
             CK(tb_launch_pair_filter_build(reinterpret_cast<const uint64_t *>(c->d_pair), nb * TB_SLOTS,
                                            c->d_filter, c->filter_word_mask, nbits, 0));
@@ -1082,7 +1089,7 @@ int tb_classifier_sector_runs(tb_classifier *c, int slot, uint64_t *n_runs)
     CK(cudaMalloc((void **)&d, sizeof *d));
     guard.mem.push_back(d);
     CK(cudaMemsetAsync(d, 0, sizeof *d, s.stream));
-    CK(tb_launch_count_sector_runs(s.view, c->k, (c->filter_word_mask >> 3) + 1, d, s.stream));
+    CK(tb_launch_count_sector_runs(s.view, c->k, (c->filter_word_mask >> 3) + 1, c->hier, d, s.stream));
     unsigned long long v = 0;
     CK(cudaMemcpyAsync(&v, d, sizeof v, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaStreamSynchronize(s.stream));
@@ -1119,7 +1126,7 @@ int tb_classifier_stats(tb_classifier *c, int slot, uint64_t *n_windows, uint64_
 
 int tb_classifier_minimizer_mode(tb_classifier *c)
 {
-    return c && c->mini ? 1 : 0;
+    return c && c->mini ? (c->hier ? 2 : 1) : 0;
 }
 
 int tb_classifier_pair_info(tb_classifier *c, uint32_t *n_buckets, uint64_t *n_distinct, int *filter_bits)

@@ -720,13 +720,35 @@ __device__ __forceinline__ uint32_t mmer_revcomp(uint32_t f, int m)
 #endif
 struct KmerCoord {
     uint32_t min_hash, fh;
+    uint32_t line_hash;  // two-level addressing only: smallest hash over the canonical 13-mers
 };
 
-__device__ __forceinline__ KmerCoord coord_of_key(uint64_t key, int k, int m)
+// Two-level ("hier") addressing for bitmaps far beyond L2 (k = 20 .. 24).  Every L1 miss on the
+// bitmap makes L2 fetch a whole 128-byte line from HBM, and the kernel's time at C3 / C5 follows
+// the number of those line fetches, i.e. the number of minimizer runs.  A second, coarser
+// minimizer -- over the k-12 canonical 13-mers of the k-mer instead of its k-m+1 m-mers -- changes
+// less often along a read (2 / (k - 11) of the windows instead of 2 / (k - m + 2)); it picks the
+// LINE, the m-mer minimizer picks the sector inside the line as before.  Neighbouring runs that
+// share their 13-mer minimizer then find their sector in L2 (the line is already there).
+#define TB_HIER_M 13
+__device__ __forceinline__ uint32_t hier_line_hash(uint64_t key, int k)
+{
+    uint32_t best = 0xFFFFFFFFu;
+    for (int i = 0; i + TB_HIER_M <= k; i++) {
+        const uint32_t f = (uint32_t)(key >> (2 * i)) & ((1u << (2 * TB_HIER_M)) - 1u);
+        const uint32_t r = mmer_revcomp(f, TB_HIER_M);
+        const uint32_t h = mmer_mix((f < r ? f : r) << (32 - 2 * TB_HIER_M));
+        best = h < best ? h : best;
+    }
+    return best;
+}
+
+__device__ __forceinline__ KmerCoord coord_of_key(uint64_t key, int k, int m, bool hier = false)
 {
     const uint32_t mmask = m == 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
     KmerCoord c;
     c.min_hash = 0xFFFFFFFFu;
+    c.line_hash = hier ? hier_line_hash(key, k) : 0u;
     uint32_t first = 0, last = 0;
     for (int i = 0; i + m <= k; i++) {
         const uint32_t f = (uint32_t)(key >> (2 * i)) & mmask;
@@ -754,6 +776,18 @@ __device__ __forceinline__ KmerCoord coord_of_key(uint64_t key, int k, int m)
 __device__ __forceinline__ uint32_t mini_word_index(uint32_t min_hash, uint32_t fh, uint32_t n_sectors)
 {
     return __umulhi(min_hash * 0xC2B2AE35u, n_sectors) * 8u + __umulhi(fh * 0x9E3779B1u, 8u);
+}
+
+// two-level form: line (4 sectors) from the 13-mer minimizer, sector in the line from the m-mer one
+__device__ __forceinline__ uint32_t hier_word_index(uint32_t line_hash, uint32_t min_hash, uint32_t fh, uint32_t n_sectors)
+{
+    return __umulhi(line_hash * 0x85EBCA6Bu, n_sectors >> 2) * 32u + __umulhi(min_hash * 0xC2B2AE35u, 4u) * 8u +
+           __umulhi(fh * 0x9E3779B1u, 8u);
+}
+
+__device__ __forceinline__ uint32_t coord_word_index(const KmerCoord &kc, uint32_t n_sectors, bool hier)
+{
+    return hier ? hier_word_index(kc.line_hash, kc.min_hash, kc.fh, n_sectors) : mini_word_index(kc.min_hash, kc.fh, n_sectors);
 }
 
 // The bits a k-mer sets in its bitmap word.  TB_BITTEST=1 takes the second position from the product
@@ -809,8 +843,11 @@ __device__ __forceinline__ uint32_t ld_filter_l1(const uint32_t *p, uint64_t pol
 #ifndef TB_MINI_MIN_BLOCKS
 #define TB_MINI_MIN_BLOCKS 6
 #endif
-template <int K, int U, int NBITS, int P2>
-__global__ void __launch_bounds__(128, TB_MINI_MIN_BLOCKS)
+template <int K, int U, int NBITS, int P2, bool HIER = false>
+#ifndef TB_HIER_MIN_BLOCKS
+#define TB_HIER_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, HIER ? TB_HIER_MIN_BLOCKS : TB_MINI_MIN_BLOCKS)
 k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint32_t *__restrict__ filter,
                      uint32_t n_sectors)
 {
@@ -855,6 +892,18 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
                 h.r_lo = c.f0 << S;
             }
 #endif
+            // two-level addressing: 13-mer hashes of the first W1-1 positions, computed directly;
+            // inside the loop the newest 13-mer of a window is the top 26 bits of its newest m-mer
+            constexpr int W1 = HIER ? K - TB_HIER_M + 1 : 1;  // 13-mers per k-mer
+            uint32_t head1[W1 > 1 ? W1 - 1 : 1];
+            if (HIER) {
+#pragma unroll
+                for (int q = 0; q < W1 - 1; q++) {
+                    const uint32_t f = (uint32_t)extract128(h.f0, h.f1, 2 * q) << (32 - 2 * TB_HIER_M);
+                    const uint32_t r = (uint32_t)extract128(h.r_lo, h.r_hi, 2 * (64 - q - TB_HIER_M)) << (32 - 2 * TB_HIER_M);
+                    head1[q] = mmer_mix(f < r ? f : r);
+                }
+            }
             // m-mer hashes of the first WC-1 positions of a half; the second half inherits them
             // from the first (its positions 16 .. 16+WC-2)
             uint32_t head[WC > 1 ? WC - 1 : 1];
@@ -874,6 +923,11 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
                 uint32_t hm[16 + WC];
 #pragma unroll
                 for (int q = 0; q < WC - 1; q++) hm[q] = head[q];
+                uint32_t hm1[16 + W1];
+                if (HIER) {
+#pragma unroll
+                    for (int q = 0; q < W1 - 1; q++) hm1[q] = head1[q];
+                }
                 uint32_t half_pass = 0;
 #pragma unroll
                 for (int g = 0; g < 16; g += U) {
@@ -885,14 +939,23 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
                     for (int u = 0; u < U; u++) {
                         const int j = g + u, q = j + WC - 1;
                         {
+                            const uint32_t raw_r = (uint32_t)extract128(h.r_lo, h.r_hi, 2 * (64 - q - MC));
 #if TB_MSCALE
                             const uint32_t f = (uint32_t)extract128(h.f0, h.f1, 2 * q) * MSCALE;
-                            const uint32_t r = (uint32_t)extract128(h.r_lo, h.r_hi, 2 * (64 - q - MC)) * MSCALE;
+                            const uint32_t r = raw_r * MSCALE;
 #else
                             const uint32_t f = (uint32_t)extract128(h.f0, h.f1, 2 * q) & MMASK;
-                            const uint32_t r = (uint32_t)extract128(h.r_lo, h.r_hi, 2 * (64 - q - MC)) & MMASK;
+                            const uint32_t r = raw_r & MMASK;
 #endif
                             hm[q] = mmer_mix(f < r ? f : r);
+                            if (HIER) {
+                                // the last 13 bases of this m-mer: the top 26 bits of the left-aligned
+                                // forward m-mer, the low 26 bits of its reverse complement
+                                static_assert(!HIER || TB_MSCALE, "two-level addressing reads the left-aligned m-mer");
+                                const uint32_t f1 = f & ~((1u << (32 - 2 * TB_HIER_M)) - 1u);
+                                const uint32_t r1 = raw_r * (1u << (32 - 2 * TB_HIER_M));
+                                hm1[j + W1 - 1] = mmer_mix(f1 < r1 ? f1 : r1);
+                            }
                         }
                         uint32_t mn = hm[j];
 #pragma unroll
@@ -906,7 +969,15 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
                         widx[u] = __umulhi(mn * 0xC2B2AE35u, n_sectors) * 8u + __umulhi(t, 8u);
 #else
                         need[u] = filter_bits<NBITS>(fh);
-                        widx[u] = mini_word_index(mn, fh, n_sectors);
+                        if (HIER) {
+                            uint32_t mn1 = hm1[j];
+#pragma unroll
+                            for (int t = 1; t + 1 < W1; t += 2) mn1 = __vimin3_u32(mn1, hm1[j + t], hm1[j + t + 1]);
+                            if ((W1 & 1) == 0) mn1 = min(mn1, hm1[j + W1 - 1]);
+                            widx[u] = hier_word_index(mn1, mn, fh, n_sectors);
+                        } else {
+                            widx[u] = mini_word_index(mn, fh, n_sectors);
+                        }
 #endif
                     }
 #pragma unroll
@@ -927,6 +998,10 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
                 pass |= half_pass << (16 * half);
 #pragma unroll
                 for (int q = 0; q < WC - 1; q++) head[q] = hm[16 + q];
+                if (HIER) {
+#pragma unroll
+                    for (int q = 0; q < W1 - 1; q++) head1[q] = hm1[16 + q];
+                }
                 // next half: drop 16 bases from the front of the span (and of its reverse complement)
                 h.f0 = (h.f0 >> 32) | (h.f1 << 32);
                 h.f1 >>= 32;
@@ -940,9 +1015,9 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
             // ---- a non-ACGT base nearby (or an unusual k): minimizer from the key itself
             for (int j = 0; j < 32; j++) {
                 if (!((c.vmask >> j) & 1u)) continue;
-                const KmerCoord kc = coord_of_key(window_key<0>(c, j, k, kmask), k, m);
+                const KmerCoord kc = coord_of_key(window_key<0>(c, j, k, kmask), k, m, HIER);
                 const uint32_t need = mini_need<NBITS>(kc.fh);
-                const uint32_t wd = ld_filter_l1(filter + mini_word_index(kc.min_hash, kc.fh, n_sectors), keep_policy);
+                const uint32_t wd = ld_filter_l1(filter + coord_word_index(kc, n_sectors, HIER), keep_policy);
                 pass |= ((wd & need) == need ? 1u : 0u) << j;
             }
         }
@@ -1053,7 +1128,7 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
 // per lane, the number of times the sector changes along its 32 windows.  Same work split and
 // same coordinates as k_classify_pair_mini, computed the slow way from each window's key.
 __global__ void __launch_bounds__(128)
-k_count_sector_runs(tb_batch_view b, int k, uint32_t n_sectors, unsigned long long *out)
+k_count_sector_runs(tb_batch_view b, int k, uint32_t n_sectors, int hier, unsigned long long *out)
 {
     const int m = tb_minimizer_m(k);
     const uint64_t kmask = (1ull << (2 * k)) - 1ull;
@@ -1066,8 +1141,9 @@ k_count_sector_runs(tb_batch_view b, int k, uint32_t n_sectors, unsigned long lo
     uint32_t prev = 0xFFFFFFFFu;
     for (int j = 0; j < 32; j++) {
         if (!((c.vmask >> j) & 1u)) continue;
-        const KmerCoord kc = coord_of_key(window_key<0>(c, j, k, kmask), k, m);
-        const uint32_t sector = __umulhi(kc.min_hash * 0xC2B2AE35u, n_sectors);
+        // two-level addressing: what reaches HBM is the LINE (its sectors are found in L2 afterwards)
+        const KmerCoord kc = coord_of_key(window_key<0>(c, j, k, kmask), k, m, hier != 0);
+        const uint32_t sector = hier ? coord_word_index(kc, n_sectors, true) >> 5 : __umulhi(kc.min_hash * 0xC2B2AE35u, n_sectors);
         if (sector != prev) runs++;
         prev = sector;
     }
@@ -1078,14 +1154,14 @@ k_count_sector_runs(tb_batch_view b, int k, uint32_t n_sectors, unsigned long lo
 template <int NBITS>
 __global__ void __launch_bounds__(256)
 k_pair_filter_build_mini(const unsigned long long *__restrict__ slots, uint64_t n_slots, uint32_t *filter,
-                         uint32_t n_sectors, int k)
+                         uint32_t n_sectors, int k, int hier)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_slots) return;
     const unsigned long long e = slots[i];
     if (e == 0) return;
-    const KmerCoord kc = coord_of_key(e & TB_PAIR_KEYMASK, k, tb_minimizer_m(k));
-    atomicOr(&filter[mini_word_index(kc.min_hash, kc.fh, n_sectors)], mini_need<NBITS>(kc.fh));
+    const KmerCoord kc = coord_of_key(e & TB_PAIR_KEYMASK, k, tb_minimizer_m(k), hier != 0);
+    atomicOr(&filter[coord_word_index(kc, n_sectors, hier != 0)], mini_need<NBITS>(kc.fh));
 }
 
 // ---- bitmap construction: one thread per table slot ---------------------------------
@@ -1323,9 +1399,21 @@ cudaError_t tb_launch_classify_pair(const tb_batch_view &b, int k, tb_pair_view 
 
 cudaError_t tb_launch_classify_pair_mini(const tb_batch_view &b, int k, tb_pair_view P,
                                          const uint32_t *filter, uint32_t n_sectors, int n_bits,
-                                         int p2_width, cudaStream_t stream)
+                                         int p2_width, int hier, cudaStream_t stream)
 {
     if (b.n_tiles == 0) return cudaSuccess;
+    if (hier) {
+        // two-level addressing (the bitmap was built with it): k = 20 .. 24, default configuration only
+        const unsigned blocks = (unsigned)((b.n_tiles + 3) / 4);
+        switch (k) {
+#define TB_HIER_CASE(KK) \
+        case KK: k_classify_pair_mini<KK, 8, 2, 2, true><<<blocks, 128, 0, stream>>>(b, k, P, filter, n_sectors); \
+                 return cudaGetLastError();
+        TB_HIER_CASE(20) TB_HIER_CASE(21) TB_HIER_CASE(22) TB_HIER_CASE(23) TB_HIER_CASE(24)
+#undef TB_HIER_CASE
+        default: return cudaErrorInvalidValue;
+        }
+    }
     switch (k) {
     case 21: return launch_pair_mini_k<21>(b, k, P, filter, n_sectors, n_bits, p2_width, stream);
     case 31: return launch_pair_mini_k<31>(b, k, P, filter, n_sectors, n_bits, p2_width, stream);
@@ -1353,24 +1441,24 @@ cudaError_t tb_launch_classify_pair_mini(const tb_batch_view &b, int k, tb_pair_
     return launch_pair_mini_k<0>(b, k, P, filter, n_sectors, n_bits, p2_width, stream);
 }
 
-cudaError_t tb_launch_count_sector_runs(const tb_batch_view &b, int k, uint32_t n_sectors,
+cudaError_t tb_launch_count_sector_runs(const tb_batch_view &b, int k, uint32_t n_sectors, int hier,
                                         unsigned long long *d_out, cudaStream_t stream)
 {
     if (b.n_tiles == 0) return cudaSuccess;
-    k_count_sector_runs<<<(unsigned)((b.n_tiles + 3) / 4), 128, 0, stream>>>(b, k, n_sectors, d_out);
+    k_count_sector_runs<<<(unsigned)((b.n_tiles + 3) / 4), 128, 0, stream>>>(b, k, n_sectors, hier, d_out);
     return cudaGetLastError();
 }
 
 cudaError_t tb_launch_pair_filter_build_mini(const uint64_t *d_pair_table, uint64_t n_slots, uint32_t *filter,
-                                             uint32_t n_sectors, int n_bits, int k, cudaStream_t stream)
+                                             uint32_t n_sectors, int n_bits, int k, int hier, cudaStream_t stream)
 {
     if (n_slots == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n_slots + 255) / 256);
     const unsigned long long *slots = reinterpret_cast<const unsigned long long *>(d_pair_table);
     if (n_bits == 2)
-        k_pair_filter_build_mini<2><<<blocks, 256, 0, stream>>>(slots, n_slots, filter, n_sectors, k);
+        k_pair_filter_build_mini<2><<<blocks, 256, 0, stream>>>(slots, n_slots, filter, n_sectors, k, hier);
     else
-        k_pair_filter_build_mini<1><<<blocks, 256, 0, stream>>>(slots, n_slots, filter, n_sectors, k);
+        k_pair_filter_build_mini<1><<<blocks, 256, 0, stream>>>(slots, n_slots, filter, n_sectors, k, hier);
     return cudaGetLastError();
 }
 

@@ -107,12 +107,13 @@ cudaError_t tb_launch_pair_filter_build(const uint64_t *d_pair_table, uint64_t n
 // p2_width = table probes per lane and phase-2 round (2 or 4)
 cudaError_t tb_launch_classify_pair_mini(const tb_batch_view &b, int k, tb_pair_view P,
                                          const uint32_t *filter, uint32_t n_sectors, int n_bits,
-                                         int p2_width, cudaStream_t stream);
+                                         int p2_width, int hier, cudaStream_t stream);
 // measurement aid: bitmap sector fetches of the batch with per-lane re-use (adds to *d_out)
-cudaError_t tb_launch_count_sector_runs(const tb_batch_view &b, int k, uint32_t n_sectors,
+cudaError_t tb_launch_count_sector_runs(const tb_batch_view &b, int k, uint32_t n_sectors, int hier,
                                         unsigned long long *d_out, cudaStream_t stream);
+// hier != 0: two-level addressing (line from the 13-mer minimizer, sector from the m-mer one)
 cudaError_t tb_launch_pair_filter_build_mini(const uint64_t *d_pair_table, uint64_t n_slots, uint32_t *filter,
-                                             uint32_t n_sectors, int n_bits, int k, cudaStream_t stream);
+                                             uint32_t n_sectors, int n_bits, int k, int hier, cudaStream_t stream);
 cudaError_t tb_launch_fixup(const tb_batch_view &b, int k, tb_set_view A, tb_set_view B,
                             cudaStream_t stream);
 cudaError_t tb_launch_finalize(const tb_batch_view &b, double scale_a, double scale_b,

@@ -599,7 +599,8 @@ class Classifier:
         _check(lib.tb_classifier_pair_info(self._h, C.byref(nb), C.byref(nd), C.byref(bits)))
         return {"log2_bits": m.value, "build_ms": ms.value, "pair_buckets": nb.value,
                 "pair_distinct": nd.value, "bits_per_key": bits.value if nb.value else 1,
-                "minimizer": bool(lib.tb_classifier_minimizer_mode(self._h))}
+                "minimizer": bool(lib.tb_classifier_minimizer_mode(self._h)),
+                "two_level": lib.tb_classifier_minimizer_mode(self._h) == 2}
 
     def stats(self, slot: int) -> dict:
         w, p, f, launches = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
