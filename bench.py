@@ -379,9 +379,13 @@ def classify_rooflines(wl, fi, windows, passes, runs, total, cls_ms, clocks, gat
                                            "counted on the device) + 32 B x windows passing the bitmap + 0.25 B x bases",
            "bitmap_sector_fetches_per_launch": runs, "fetches_per_window": runs / max(1, windows),
            "traffic": ncu.get("dram_bytes_per_launch"), "traffic_source": ncu.get("source"),
-           "random_fetches_per_s": (runs + passes) / cls_s,
-           "random_sector_ceiling_per_s": gather.get("dram"),
-           "frac_of_random_sector_ceiling": ((runs + passes) / cls_s / gather["dram"]) if gather.get("dram") else None}
+           "random_sector": {
+               "what": "random 32-B sector fetches the kernel needs (bitmap runs + table probes) per second against "
+                       "the measured ceiling for uniformly random sectors of a table of the bitmap's size; above 1 "
+                       "where neighbouring misses share a 128-B line that L2 fetches whole",
+               "achieved_per_s": (runs + passes) / cls_s, "ceiling_per_s": gather.get("dram"),
+               "ceiling_table_bytes": gather.get("dram_table_bytes"),
+               "frac": ((runs + passes) / cls_s / gather["dram"]) if gather.get("dram") else None}}
     if ncu.get("dram_bytes_per_launch"):
         # the captured launch's own traffic over ITS duration: how busy HBM really is
         hbm["traffic_gbs_at_capture"] = ncu["dram_bytes_per_launch"] / (ncu["duration_ms"] * 1e-3) / 1e9
@@ -667,10 +671,16 @@ def run_gpu_arm(args, rank, local_rank, world):
     if rank == 0:
         gather = {}
         if not args.no_gather:
-            # random-32-B-sector request ceilings of THIS GPU, same run: a table far larger
-            # than L2 (HBM random-access bound) and one that stays L2-resident
-            gather["dram"] = max(kmers.gather_bench(4 << 30, mlp, tpb, bps, 48, 0)[0]
-                                 for mlp, tpb, bps in ((8, 256, 8), (16, 256, 4), (4, 512, 4)))
+            # random-32-B-sector request ceilings of THIS GPU, same run (the denominator north_star
+            # names): uniformly random sectors of a table as large as this workload's bitmap (4 GB if
+            # the bitmap is L2-resident), read with the kernel's own bitmap load (32-bit, allocating in
+            # L1, evict_last in L2) and with the 256-bit bucket load; the rate does not depend on the
+            # load flavour, the loads in flight or the launch shape (profiles/r2_gather_ceiling.jsonl)
+            bitmap_bytes = (1 << finfo["log2_bits"]) // 8 if finfo["log2_bits"] else 0
+            table = bitmap_bytes if bitmap_bytes >= (256 << 20) else (4 << 30)
+            gather["dram"] = max(kmers.gather_bench(table, mlp, tpb, bps, 48, variant)[0]
+                                 for variant in (13, 0) for mlp, tpb, bps in ((8, 256, 8), (16, 256, 4)))
+            gather["dram_table_bytes"] = table
             gather["l2"] = max(kmers.gather_bench(32 << 20, mlp, tpb, bps, 256, 0)[0]
                                for mlp, tpb, bps in ((8, 256, 8), (16, 256, 4), (8, 128, 16)))
         roofline = classify_rooflines(wl, finfo, windows, passes, runs, total, cls_ms / args.steps, clocks, gather)

@@ -87,3 +87,24 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "liboracle" not in text and "_ref/" not in text, f
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/trio_kmers_b200.h is the drop-in boundary: it must compile as C99 (no C++, no CUDA
+    types) and declare the reference's symbols with the reference's signatures (c/kmers.c:50,74,185,270)."""
+    import shutil
+    import subprocess
+
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "use_header.c"
+    src.write_text(
+        '#include "trio_kmers_b200.h"\n'
+        "hash_set *(*p_create)(char *) = create_kmer_hash_set;\n"
+        "void (*p_count)(char *, hash_set *, hash_set *, int *, int *) = count_kmers_in_read;\n"
+        "uint64_t (*p_k2i)(char *, unsigned char) = kmer_to_int;\n"
+        "void (*p_rc)(char *, char *, unsigned char) = reverse_complement;\n"
+        "char (*p_in)(char *, char *, hash_set *) = kmer_in_hash_set;\n"
+        "int f(const tb_stream_options *o) { return o->n_devices + (int)sizeof(tb_packed_batch) + (int)sizeof(tb_stream_stats); }\n")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                    "-o", str(tmp_path / "use_header.o")], check=True)
