@@ -412,6 +412,9 @@ def classify_rooflines(wl, fi, windows, passes, runs, total, cls_ms, clocks, gat
                                                 "(it stays in L2: its sector fetches are not HBM traffic)")
         if ncu.get("dram_bytes_per_launch"):
             hbm["traffic_over_algorithmic"] = ncu["dram_bytes_per_launch"] / hbm_bytes
+        rs = hbm["random_sector"]  # only the table probes reach HBM here
+        rs["achieved_per_s"] = passes / cls_s
+        rs["frac"] = (passes / cls_s / gather["dram"]) if gather.get("dram") else None
     main = hbm
     if alu and alu["frac"] > (hbm.get("traffic_frac_of_peak_at_capture") or hbm["frac"]):
         main = alu
