@@ -494,9 +494,9 @@ def _write_fastq(path, bases, offsets, rng, width=0):
 
 
 def test_native_pipeline_equals_python_io(kmers, capsys, tmp_path):
-    """Same input through the native pipeline (default: 2-bit batches, every visible GPU, FASTQ-aware
-    gzip encoder), the same with zlib only, forced onto one GPU and onto two workers' worth of
-    devices, and the Python reader/writer (--python-io) -- in gzip and in plain mode (the
+    """Same input through the native pipeline (default: 2-bit batches, one GPU, FASTQ-aware gzip
+    encoder), the same with zlib only, on every visible GPU, on two, with three device workers, and
+    through the Python reader/writer (--python-io) -- in gzip and in plain mode (the
     reference's --no-gzip-output with its two-handles artefact, seq.py:127-130): identical TSV and
     identical (decompressed) outputs, several batches."""
     import random
@@ -515,7 +515,7 @@ def test_native_pipeline_equals_python_io(kmers, capsys, tmp_path):
     for plain in (False, True):
         outs = {}
         for mode, extra in (("native", []), ("python", ["--python-io"]), ("native_zlib", ["--no-fastq-gzip"]),
-                            ("native_1gpu", ["--gpus", "1"]), ("native_2gpu", ["--gpus", "2"]),
+                            ("native_all_gpus", ["--gpus", "0"]), ("native_2gpu", ["--gpus", "2"]),
                             ("native_3workers", ["--gpu-workers", "3"])):
             d = tmp_path / f"{mode}_{plain}"
             d.mkdir()

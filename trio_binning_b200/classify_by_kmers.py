@@ -43,9 +43,11 @@ _B200_ARGUMENTS = (
     (("--python-io",), dict(action="store_true", default=False,
                             help="read and write FASTA/FASTQ in Python like the reference instead of the "
                                  "native multi-threaded pipeline (B200 addition; same output, one GPU)")),
-    (("--gpus",), dict(type=int, default=0,
+    (("--gpus",), dict(type=int, default=1,
                        help="number of GPUs to spread the batches over, 0 = all visible ones; the sets are "
-                            "replicated on each, the output does not depend on it (B200 addition)")),
+                            "replicated on each, the output does not depend on it. One B200 classifies about a "
+                            "hundred times faster than one host parses FASTQ, so more GPUs only pay off when the "
+                            "reads come from something faster than a file (B200 addition)")),
     (("--gpu-workers",), dict(type=int, default=0,
                               help="device worker threads of the pipeline, 0 = one per GPU used; more than that wrap "
                                    "around the GPUs, each worker with its own replica of the sets (B200 addition; "
