@@ -681,15 +681,18 @@ def python_text_io_behaviour(directory: str = ".") -> Tuple[int, int]:
     # different releases): fill a binary file in 512-byte steps; the first write that does not
     # fit makes the buffer flush, and the file is then exactly one buffer long
     buffer_size = 0
-    with tempfile.TemporaryDirectory(dir=directory) as tmp:
-        path = os.path.join(tmp, "probe")
-        with open(path, "wb") as f:
-            piece = b"x" * 512
-            for _ in range((16 << 20) // 512 + 2):
-                f.write(piece)
-                buffer_size = os.fstat(f.fileno()).st_size
-                if buffer_size:
-                    break
+    try:
+        with tempfile.TemporaryDirectory(dir=directory) as tmp:
+            path = os.path.join(tmp, "probe")
+            with open(path, "wb") as f:
+                piece = b"x" * 512
+                for _ in range((16 << 20) // 512 + 2):
+                    f.write(piece)
+                    buffer_size = os.fstat(f.fileno()).st_size
+                    if buffer_size:
+                        break
+    except OSError:
+        buffer_size = 0  # cannot probe there: the writer falls back to the file's st_blksize
     return _PY_TEXT_IO, buffer_size
 
 
