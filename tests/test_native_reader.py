@@ -51,6 +51,10 @@ def test_native_reader_newline_flavours(kmers, seq, tmp_path):
         "mixed": b">r1\nAC\r\nGT\rTT\n@q\nAA\n+\n!!\n",
         "cr_at_chunk_edge": b">r1\n" + b"A" * 70 + b"\r\n" + b"C" * 10 + b"\r",
         "utf8_name": ">résumé x\nACGT\n".encode(),
+        # Python counts CHARACTERS when it decides where a quality block ends (seq.py:75-80)
+        "utf8_seq_and_qual": "@r1\nACéGT\n+\n!!é!!\n@r2\nAC\n+\n!!\n".encode(),
+        "utf8_qual_two_lines": "@r1\nACGTAC\n+\né!!\n!!é\n>r2\nGG\n".encode(),
+        "utf8_qual_longer_in_bytes": "@r1\nACGT\n+\nééé\né\n@r2\nAC\n+\n!!\n".encode(),
         "fastq_no_final_newline": b"@r1\nACGT\n+\n!!!!",
         "plus_only_at_eof": b"@r1\nACGT\n+",
         "header_only_at_eof": b">",

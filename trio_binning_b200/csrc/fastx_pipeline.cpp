@@ -98,6 +98,7 @@ public:
     bool next(const char *&data, size_t &len)
     {
         bool spilled = false;
+        line_ascii_ = true;
         for (;;) {
             if (pos_ == len_ && !fill()) {
                 if (!spilled || spill_.empty()) return false;
@@ -105,6 +106,7 @@ public:
                 len = spill_.size();
                 return true;
             }
+            line_ascii_ = line_ascii_ && cur_ascii_;
             if (pending_cr_) {
                 // a '\r' ended the previous line; swallow the '\n' of a "\r\n" pair
                 pending_cr_ = false;
@@ -118,7 +120,8 @@ public:
             // first '\n' or '\r' (two vectorised scans; '\r' is looked for only up to the '\n')
             const char *nl = (const char *)memchr(p, '\n', avail);
             size_t i = nl ? (size_t)(nl - p) : avail;
-            if (const char *cr = (const char *)memchr(p, '\r', i)) i = (size_t)(cr - p);
+            if (cur_has_cr_)
+                if (const char *cr = (const char *)memchr(p, '\r', i)) i = (size_t)(cr - p);
             pos_ += i;
             if (i < avail) {
                 if (p[i] == '\r') {
@@ -144,6 +147,9 @@ public:
             spill_.append(p, i);
         }
     }
+    // true if every byte of the line next() returned last is a character of its own (no UTF-8
+    // multi-byte sequences): its character count is its length
+    bool line_ascii() const { return line_ascii_; }
     uint64_t bytes_in() const { return bytes_in_; }
     // time spent inside the inflate (summed over the decoding threads; 0 for plain input)
     double inflate_seconds() const { return (double)inflate_ns_.load() * 1e-9; }
@@ -166,6 +172,26 @@ private:
         std::vector<unsigned char> comp;  // BGZF task: the compressed blocks
         size_t expect = 0;                //            and the sum of their ISIZE fields
         std::string why;
+        // what the parser may skip in this chunk: the search for '\r' line ends and the UTF-8
+        // character count (every byte is a character).  Scanned once per chunk -- by the thread
+        // that produced it when that thread has time to spare (plain files, BGZF workers), else by
+        // the parser when it takes the chunk (a serial inflate is the bottleneck already)
+        bool flags_known = false, has_cr = true, ascii = false;
+        void scan_flags()
+        {
+            const char *p = data.data();
+            has_cr = memchr(p, '\r', len) != nullptr;
+            uint64_t acc = 0;
+            size_t i = 0;
+            for (; i + 8 <= len; i += 8) {
+                uint64_t w;
+                memcpy(&w, p + i, 8);
+                acc |= w;
+            }
+            for (; i < len; i++) acc |= (uint64_t)(unsigned char)p[i];
+            ascii = (acc & 0x8080808080808080ull) == 0;
+            flags_known = true;
+        }
     };
     using ChunkPtr = std::shared_ptr<Chunk>;
 
@@ -194,6 +220,7 @@ private:
             free_.pop_back();
             c->len = c->expect = 0;
             c->done = c->failed = false;
+            c->flags_known = false;
             c->comp.clear();
             c->why.clear();
             return c;
@@ -251,6 +278,7 @@ private:
                 return;
             }
             c->len = (size_t)got;
+            if (!gz_) c->scan_flags();  // read() leaves this thread idle most of the time
             c->done = true;
             if (!enqueue(c, false)) return;
         }
@@ -362,6 +390,7 @@ private:
             inflate_ns_.fetch_add((uint64_t)(seconds_since(t_dec) * 1e9));
             c->len = n;
             c->failed = bad;
+            if (!bad) c->scan_flags();
             finish(c);
         }
     }
@@ -409,6 +438,10 @@ private:
             cur_ = c->data.data();
             pos_ = 0;
             len_ = c->len;
+            lk.unlock();
+            if (!c->flags_known) c->scan_flags();
+            cur_has_cr_ = c->has_cr;
+            cur_ascii_ = c->ascii;
             return true;
         }
     }
@@ -426,6 +459,7 @@ private:
     size_t max_in_flight_ = 3;
     ChunkPtr cur_chunk_;
     std::string spill_;  // a line that straddles chunks
+    bool cur_has_cr_ = true, cur_ascii_ = false, line_ascii_ = false;
     char *cur_ = nullptr;
     size_t pos_ = 0, len_ = 0;
     uint64_t bytes_in_ = 0, bgzf_bytes_ = 0;
@@ -634,7 +668,7 @@ struct Reader {
             const uint32_t name_len = (uint32_t)(cur->text.size() - name_off);
             // ---- sequence lines until a line starting with '@', '+' or '>'
             seq_start = fill = cur->total();
-            bool got_marker = false;
+            bool got_marker = false, seq_ascii = true;
             while (src.next(lp, ln)) {
                 const char c = lp[0];
                 if (c == '@' || c == '+' || c == '>') {
@@ -648,6 +682,7 @@ struct Reader {
                 }
                 memcpy(cur->bases + fill, lp, n);
                 fill += (int64_t)n;
+                seq_ascii = seq_ascii && src.line_ascii();
             }
             if (!ok) break;
             const int64_t seq_len = fill - seq_start;
@@ -661,14 +696,14 @@ struct Reader {
             }
             // ---- FASTQ: quality lines, straight into the batch's text, until at least len(seq)
             // ---- CHARACTERS were read
-            const size_t seq_chars = n_chars(cur->bases + seq_start, (size_t)seq_len);
+            const size_t seq_chars = seq_ascii ? (size_t)seq_len : n_chars(cur->bases + seq_start, (size_t)seq_len);
             const uint64_t qual_off = cur->text.size();
             size_t have = 0;
             bool complete = false;
             while (src.next(lp, ln)) {
                 const size_t n = chop_len(lp, ln);
                 cur->text.append(lp, n);
-                have += n_chars(lp, ln) - 1;
+                have += (src.line_ascii() ? ln : n_chars(lp, ln)) - 1;
                 if (have >= seq_chars) {
                     complete = true;
                     break;
