@@ -15,7 +15,7 @@ FMA = {"IMAD", "FFMA", "FMUL", "FADD"}
 def main(obj, k="21"):
     sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
     blocks = sass.split("Function : ")
-    body = next(b for b in blocks if f"pair_miniILi{k}ELi8ELi2ELi2" in b.split("\n")[0])
+    body = next(b for b in blocks if f"pair_miniILi{k}ELi8ELi2ELi2ELb0" in b.split("\n")[0])
     ins = []
     for line in body.splitlines():
         m = re.match(r"\s+/\*([0-9a-f]+)\*/\s+(@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
