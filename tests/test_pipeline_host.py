@@ -179,3 +179,25 @@ def test_gpu_code_path_of_the_pipeline_with_stubbed_classifier(tmp_path):
                     h.update(gzip.decompress(raw) if mode == "gz" else raw)
             digests.setdefault(mode, set()).add(h.hexdigest())
     assert len(digests["gz"]) == 1 and len(digests["plain"]) == 1
+
+
+def test_plain_writer_random_shapes_against_cpython(kmers, seq, tmp_path):
+    """Randomised version of the plain-output test: record sizes drawn around the writers' thresholds
+    (the text layer's 8192-byte chunk, the buffer's st_blksize, multiples of both), random bins."""
+    import random
+
+    rng = random.Random(20261017)
+    marks = [1, 50, 150, 2040, 2048, 4090, 4096, 4100, 8180, 8192, 8200, 12288, 16384, 30000]
+    for trial in range(8):
+        lengths = [max(1, rng.choice(marks) + rng.randrange(-12, 13)) for _ in range(rng.randrange(5, 120))]
+        bins = "".join(rng.choice("ABU" if trial % 2 else "AB") for _ in range(rng.randrange(1, 40)))
+        tmp = str(tmp_path / f"t{trial}")
+        os.makedirs(tmp)
+        reads = os.path.join(tmp, "reads.fq")
+        _fastx(reads, lengths, seed=trial, fasta_every=rng.choice([0, 3, 7]))
+        want_dir, want_tsv = _python_writer(seq, reads, bins, tmp, False, ".fq")
+        got_dir, got_tsv, _ = _native(kmers, reads, bins, tmp, "native", False, ".fq", batch_bases=rng.choice([1, 5000, 1 << 20]),
+                                      workers=rng.choice([1, 2, 4]))
+        for name in os.listdir(want_dir):
+            assert _content(os.path.join(got_dir, name), False) == _content(os.path.join(want_dir, name), False), (trial, name, bins)
+        assert got_tsv == want_tsv
