@@ -323,18 +323,20 @@ __device__ __forceinline__ void lane_setup(const tb_batch_view &b, int64_t tile,
         if (c.fast) {
             c.vmask = 0xFFFFFFFFu;
         } else {
+            // One step per READ that overlaps the lane's 32 positions (two for 150-bp reads), not
+            // one per position: read [s, e) contributes the window starts from s + skip to e - k.
             int64_t rr = r, s = start, e = end;
-            uint32_t sk = b.skip[rr];
-            for (int j = 0; j < 32; j++) {
-                const int64_t pos = c.p0 + j;
-                if (pos >= b.total_bases) break;
-                while (e <= pos) {
-                    rr++;
-                    s = e;
-                    e = off[rr + 1];
-                    sk = b.skip[rr];
+            const int64_t last = c.p0 + 31;
+            for (;;) {
+                const int64_t lo = max(s + (int64_t)b.skip[rr], c.p0), hi = min(e - k, last);
+                if (hi >= lo) {
+                    const uint32_t n = (uint32_t)(hi - lo + 1);
+                    c.vmask |= (n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u)) << (uint32_t)(lo - c.p0);
                 }
-                if (pos + k <= e && (uint64_t)(pos - s) >= (uint64_t)sk) c.vmask |= 1u << j;
+                if (e > last || e >= b.total_bases) break;
+                rr++;
+                s = e;
+                e = off[rr + 1];
             }
         }
     }
