@@ -291,8 +291,11 @@ __device__ __forceinline__ uint64_t window_key(const LaneCtx &c, int j, int k, u
     return fwd < rc ? fwd : rc;
 }
 
-__device__ __forceinline__ void lane_setup(const tb_batch_view &b, int64_t tile, int lane, int k,
-                                           LaneCtx &c)
+// lane_setup in two parts.  lane_stream: the lane's 64 bases of both streams -- all phase 1 of the
+// minimizer kernel needs.  lane_bounds: which of its 32 windows lie inside one read (and past the
+// read's Q3-UB replay), a chain of dependent loads (tile -> read -> offsets -> skip) whose latency
+// that kernel hides behind phase 1 by asking for it afterwards.
+__device__ __forceinline__ void lane_stream(const tb_batch_view &b, int64_t tile, int lane, LaneCtx &c)
 {
     const int64_t w = tile * 32 + lane;
     c.p0 = w * 32;
@@ -307,7 +310,14 @@ __device__ __forceinline__ void lane_setup(const tb_batch_view &b, int64_t tile,
     // reverse complement of the span: base s of the span sits at base 63-s
     c.r_lo = tb_revcomp64(e1);
     c.r_hi = tb_revcomp64(e0);
+    c.r = 0;  // until lane_bounds says otherwise: no window of this lane exists
+    c.end = 0;
+    c.vmask = 0;
+    c.fast = false;
+}
 
+__device__ __forceinline__ void lane_bounds(const tb_batch_view &b, int64_t tile, int k, LaneCtx &c)
+{
     const int64_t *__restrict__ off = b.offsets;
     c.r = 0;
     c.end = 0;
@@ -340,6 +350,12 @@ __device__ __forceinline__ void lane_setup(const tb_batch_view &b, int64_t tile,
             }
         }
     }
+}
+
+__device__ __forceinline__ void lane_setup(const tb_batch_view &b, int64_t tile, int lane, int k, LaneCtx &c)
+{
+    lane_stream(b, tile, lane, c);
+    lane_bounds(b, tile, k, c);
 }
 
 // Add the lane's hits to the per-read counters.
@@ -862,13 +878,17 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
     const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tile >= b.n_tiles) return;  // warp-uniform
     LaneCtx c;
-    lane_setup(b, tile, lane, k, c);
+    lane_stream(b, tile, lane, c);
     uint64_t keep_policy;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
+    // the general path below walks the windows one by one and wants to know which exist; the
+    // unrolled path computes all 32 and masks afterwards, while the read boundaries arrive
+    const bool unrolled = K != 0 && c.clean;
+    if (!unrolled) lane_bounds(b, tile, k, c);
 
     uint32_t pass = 0;
-    if (c.vmask) {
-        if (K != 0 && c.clean) {
+    if (unrolled ? c.p0 < b.total_bases : c.vmask != 0) {
+        if (unrolled) {
             // ---- all bases valid: m-mer hashes straight from the two streams, sliding minimum.
             // Two passes of 16 windows over the same unrolled body (the second on the span
             // moved by 16 bases) keep the loop inside the instruction cache.
@@ -1013,6 +1033,7 @@ k_classify_pair_mini(tb_batch_view b, int k_runtime, tb_pair_view P, const uint3
 #if TB_REVODD
             if (lane & 1) pass = __brev(pass);
 #endif
+            lane_bounds(b, tile, k, c);
         } else {
             // ---- a non-ACGT base nearby (or an unusual k): minimizer from the key itself
             for (int j = 0; j < 32; j++) {
