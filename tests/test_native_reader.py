@@ -285,3 +285,27 @@ def test_bgzf_writer_round_trip(kmers, tmp_path):
     empty.write_bytes(b"")
     kmers.gzip_copy(str(empty), str(tmp_path / "e.gz"), bgzf=True)
     assert gzip.decompress((tmp_path / "e.gz").read_bytes()) == b""
+
+
+def test_mixed_newlines_and_utf8_everywhere(kmers, seq, tmp_path):
+    """A file that mixes "\\n", "\\r\\n" and "\\r" line ends record by record, has tabs in names and
+    multi-byte characters in sequences and qualities (Python counts characters, not bytes, when it
+    decides where a quality block ends): same records as the Python reader, plain and gzipped."""
+    rng = random.Random(5)
+    parts = []
+    for i in range(3000):
+        n = rng.choice([1, 30, 150, 5000])
+        s = "".join(rng.choice("ACGTNacgté") for _ in range(n))
+        q = "".join(rng.choice("!#5Iéü") for _ in range(n))
+        nl = rng.choice(["\n", "\r\n", "\r"])
+        parts.append(f">f{i} x{nl}{s}{nl}" if i % 5 == 0 else f"@r{i}\tt c{nl}{s}{nl}+{nl}{q}{nl}")
+    raw = "".join(parts).encode()
+    plain = tmp_path / "mixed.fastq"
+    plain.write_bytes(raw)
+    want = _python_records(seq, plain)
+    assert len(want) > 2000
+    assert kmers.fastx_dump(str(plain)) == want
+    gz = tmp_path / "mixed.fastq.gz"
+    with gzip.open(gz, "wb", compresslevel=1) as f:
+        f.write(raw)
+    assert kmers.fastx_dump(str(gz)) == want
