@@ -109,6 +109,18 @@ int use_device(int device)
     return 0;
 }
 
+// m of the minimizer scheme (same rule as tb_minimizer_m in classify.cu; checked by a test that
+// compares bitmap sizes, and by every parity test: build and look-up share the device function)
+int tb_minimizer_m_host(int k)
+{
+    if (k >= 22) return 16;
+    int m = k - 6;
+    const int floor13 = k - 2 < 13 ? k - 2 : 13;
+    if (m < floor13) m = floor13;
+    const int half = (k + 1) / 2;
+    return m > half ? m : half;
+}
+
 tb_set_view view_of(const hash_set *s)
 {
     tb_set_view v;
@@ -462,9 +474,21 @@ int build_filter(tb_classifier *c)
     if (m < 0) {
         const uint64_t n = c->A->n_distinct + c->B->n_distinct;
         if (c->mini) {
-            // >= 16 bits per key, 2^16 .. 2^35 bits (4 GB): C2 2^29, C3 2^33, C4 2^34
+            // Bits per key, measured (profiles/r2_bitmap_size_sweep.txt): a larger bitmap lets fewer
+            // non-members through to the table probes, a smaller one keeps more of its sectors in
+            // L2.  With few m-mers per window (k <= 23: a sector fetch every ~4 windows) the
+            // fetches dominate and ~8-16 bits per key are best (C3 2^32, C5 2^30); with many
+            // (k >= 28: a fetch every ~8 windows) the survivors do, and 32+ bits per key win
+            // (C4 2^35).  A bitmap that fits L2 anyway (<= 2^29 bits = 64 MB) may as well be
+            // sparse: up to 32 bits per key (C2 2^29).
+            const int w = c->k - tb_minimizer_m_host(c->k) + 1;
+            const uint64_t per_key = w <= 8 ? 8 : (w <= 12 ? 16 : 32);
             m = 16;
-            while (m < 35 && (1ull << m) < 16 * n) m++;
+            while (m < 35 && (1ull << m) < per_key * n) m++;
+            if (m < 29) {
+                m = 16;
+                while (m < 29 && (1ull << m) < 32 * n) m++;
+            }
         } else {
             // hash-addressed words: keep the bitmap L2-resident (<= 2^29 bits = 64 MB); very
             // large sets do better with 2^30 although it spills
