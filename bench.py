@@ -5,7 +5,7 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
 
 Workload (config.workload = "c3"): BASELINE.json configs[2] at its full SET sizes -- 150 M + 150 M
-distinct 21-mers (4.8 GB tagged table + 1 GB bitmap per GPU) -- and, per step and per GPU, a slice
+distinct 21-mers (4.8 GB tagged table + 0.5 GB bitmap per GPU) -- and, per step and per GPU, a slice
 of its reads: 10 000 synthetic long reads (gamma lengths, mean 25 kb, ~0.25 Gbases).  Weak
 scaling: every rank classifies its own reads against its own replica of both sets; no collective
 on the data path.  configs[1], [3] and [4] (c2, c4, c5) are measured beside it at N = 1
