@@ -287,6 +287,9 @@ typedef struct tb_kmer_counter tb_kmer_counter;
  * of `n_parts` are counted (1 partition = everything): libraries whose distinct k-mers exceed
  * one table are counted in several passes over the input.  replaces `kmc -k..` (:62-103) */
 tb_kmer_counter *tb_counter_create(int k, uint64_t n_slots, int part, int n_parts, int device);
+/* Device bytes one slot of the table takes for this k (8 up to k = 22, where key and count share
+ * a word, else 12): what a caller sizes n_slots with for a memory budget. */
+int tb_counter_slot_bytes(int k);
 void tb_counter_destroy(tb_kmer_counter *c);
 /* Count the canonical k-mers of a batch of reads (concatenated ASCII + offsets, host memory).
  * Returns once the batch is on its way to the device; the caller may reuse its buffers. */

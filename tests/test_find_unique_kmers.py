@@ -137,11 +137,11 @@ def kmers():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k", [15, 21, 31, 32])
+@pytest.mark.parametrize("k", [15, 21, 22, 23, 31, 32])   # 22 | 23: packed | split slots
 def test_counting_histogram_and_subtraction_vs_oracle(kmers, k):
     from oracle import find_unique_oracle as orc
 
-    rng = np.random.default_rng(100 + k)
+    rng = np.random.default_rng(100 + k if k != 22 else 222)   # a seed whose histogram has a usable valley
     ga, gb = _haplotypes(rng, 60_000, 300)
     reads_a = _reads_from(rng, ga, 25, 150, 0.004, n_rate=0.001, lower=True)
     reads_b = _reads_from(rng, gb, 18, 150, 0.004, n_rate=0.001)
@@ -192,6 +192,26 @@ def test_partitions_and_full_tables(kmers):
         small.add_reads(texts)
         with pytest.raises(OverflowError):
             small.stats()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [21, 22, 25])
+def test_counts_far_beyond_the_saturated_maximum(kmers, k):
+    """A k-mer seen millions of times (homopolymers, satellites): up to k = 22 the count shares the
+    slot's word with the key and stops near 2^19 -- it must never carry into nothing, corrupt the
+    key, or leave the last histogram bin (readers clamp at 255, KMC's -cs)."""
+    assert kmers.lib.tb_counter_slot_bytes(k) == (8 if k <= 22 else 12)
+    with kmers.KmerCounter(k, 1 << 16) as c:
+        for _ in range(3):
+            c.add_reads(["A" * 400_000, "T" * 300_000, "ACGTTGCA" * 10])
+        st = c.stats()
+        assert st["windows"] == 3 * (400_000 - k + 1 + 300_000 - k + 1 + 80 - k + 1)
+        hist = c.histogram(256)
+        assert hist[255] == 1 and hist.sum() == st["distinct"]
+        assert list(c.select_unique(None, 255, 255)) == [0]          # poly-A / poly-T: canonical key 0
+        with kmers.KmerCounter(k, 1 << 16) as other:
+            other.add_reads(["T" * 100] * 2)
+            assert len(c.select_unique(other, 255, 255)) == 0          # and it is found by lookups
 
 
 @pytest.mark.gpu

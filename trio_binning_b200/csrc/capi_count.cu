@@ -43,6 +43,7 @@ struct tb_kmer_counter {
     tb_count_view T;
     unsigned long long *d_stats = nullptr;  // windows counted, distinct keys, overflow flag
     cudaStream_t stream = nullptr;
+    cudaEvent_t copied = nullptr;           // the batch's host buffers have been read
     // batch buffers (grown on demand)
     unsigned char *d_ascii = nullptr;
     int64_t *d_offsets = nullptr;
@@ -88,6 +89,8 @@ int ensure_batch_buffers(tb_kmer_counter *c, int64_t total, int64_t n_reads)
 
 extern "C" {
 
+int tb_counter_slot_bytes(int k) { return k <= TB_COUNT_PACKED_MAX_K ? 8 : 12; }
+
 tb_kmer_counter *tb_counter_create(int k, uint64_t n_slots, int part, int n_parts, int device)
 {
     if (k < 1 || k > 32) { cfail("k=%d outside 1..32", k); return nullptr; }
@@ -101,16 +104,19 @@ tb_kmer_counter *tb_counter_create(int k, uint64_t n_slots, int part, int n_part
     c->T.n_slots = n_slots;
     c->T.part = (uint32_t)part;
     c->T.n_parts = (uint32_t)n_parts;
+    const bool packed = k <= TB_COUNT_PACKED_MAX_K;
+    c->T.count_shift = packed ? 2u * (uint32_t)k : 0u;
     bool ok = cudaMalloc((void **)&c->T.keys, n_slots * 8) == cudaSuccess &&
-              cudaMalloc((void **)&c->T.counts, n_slots * 4) == cudaSuccess &&
+              (packed || cudaMalloc((void **)&c->T.counts, n_slots * 4) == cudaSuccess) &&
               cudaMalloc((void **)&c->d_stats, 4 * 8) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+              cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->copied, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMemset(c->T.keys, 0xFF, n_slots * 8) == cudaSuccess &&
-         cudaMemset(c->T.counts, 0, n_slots * 4) == cudaSuccess && cudaMemset(c->d_stats, 0, 4 * 8) == cudaSuccess &&
-         cudaDeviceSynchronize() == cudaSuccess;
+         (packed || cudaMemset(c->T.counts, 0, n_slots * 4) == cudaSuccess) &&
+         cudaMemset(c->d_stats, 0, 4 * 8) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) {
         cfail("k-mer counter: cannot allocate a table of %llu slots (%.1f GB): %s", (unsigned long long)n_slots,
-              (double)n_slots * 12 / 1e9, cudaGetErrorString(cudaGetLastError()));
+              (double)n_slots * tb_counter_slot_bytes(k) / 1e9, cudaGetErrorString(cudaGetLastError()));
         tb_counter_destroy(c);
         return nullptr;
     }
@@ -127,6 +133,7 @@ void tb_counter_destroy(tb_kmer_counter *c)
     if (c->T.counts) cudaFree(c->T.counts);
     if (c->d_stats) cudaFree(c->d_stats);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copied) cudaEventDestroy(c->copied);
     delete c;
 }
 
@@ -142,10 +149,12 @@ int tb_counter_add_batch(tb_kmer_counter *c, const char *bases, const int64_t *o
     if (total == 0) return 0;
     CKC(cudaSetDevice(c->device));
     if (ensure_batch_buffers(c, total, n_reads)) return -1;
-    // pageable sources are staged by the runtime before the call returns, so the caller may
-    // reuse its buffers; the kernels then overlap with the parsing of the next batch
+    // The caller may reuse its buffers when this returns: pageable sources are staged by the runtime
+    // before cudaMemcpyAsync returns, page-locked ones are read by the copy engine later, so those
+    // are waited for (the copy only).  The kernels overlap with the parsing of the next batch.
     CKC(cudaMemcpyAsync(c->d_ascii, bases, (size_t)total, cudaMemcpyHostToDevice, c->stream));
     CKC(cudaMemcpyAsync(c->d_offsets, offsets, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CKC(cudaEventRecord(c->copied, c->stream));
     tb_batch_view v;
     memset(&v, 0, sizeof v);
     v.ascii = c->d_ascii;
@@ -159,6 +168,7 @@ int tb_counter_add_batch(tb_kmer_counter *c, const char *bases, const int64_t *o
     v.fold_case = 1;
     CKC(tb_launch_pack(v, c->k, c->stream));
     CKC(tb_launch_count_windows(c->d_F, c->d_V, c->d_offsets, n_reads, total, c->k, c->T, c->d_stats, c->stream));
+    CKC(cudaEventSynchronize(c->copied));
     return 0;
 }
 

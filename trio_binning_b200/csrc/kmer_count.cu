@@ -19,9 +19,16 @@
 // window and of its reverse complement (the classify kernels' encoding, c/kmers.c:50-72):
 //   msb(window) = ~rc & mask,  msb(revcomp) = ~fwd & mask,  canonical = ~max(fwd, rc) & mask.
 //
-// Table: open addressing, linear probing, keys[] (u64, empty = ~0: no canonical key is all ones,
-// its partner would be 0) and counts[] (u32); insert = atomicCAS on the key, atomicAdd on the
-// count.  HBM random-atomic bound; the host parser is far slower than this kernel.
+// Table: open addressing, linear probing, empty = ~0 (no canonical key is all ones, its partner
+// would be 0).  Two layouts:
+//   packed (k <= 22, the reference's default k = 21 included): ONE 64-bit word per slot, the key in
+//     its low 2k bits and the count above it; insert = atomicCAS(empty -> key | 1 << 2k), count =
+//     one 64-bit atomic add on the same word.  8 bytes per slot and one random sector per window.
+//     The count stops near 2^19 (readers clamp at 255, far below) so that it never carries out.
+//   split (k >= 23): keys[] (u64) and counts[] (u32), atomicCAS on the key, atomicAdd on the count;
+//     12 bytes per slot, two random sectors per window.
+// Bound by random 32-byte sector accesses to HBM (each one a 128-byte line fetch); the
+// slot size matters beyond the kernel: it sets how many passes over the input a genome needs.
 #include "launchers.h"
 
 namespace {
@@ -29,6 +36,16 @@ namespace {
 __device__ __forceinline__ uint64_t count_slot_of(uint64_t key, uint64_t n_slots)
 {
     return __umul64hi(tb_hash64(key), n_slots);
+}
+
+// key and count of an occupied slot in either layout
+__device__ __forceinline__ uint64_t slot_key(const tb_count_view &T, unsigned long long word)
+{
+    return T.count_shift ? word & ((1ull << T.count_shift) - 1ull) : word;
+}
+__device__ __forceinline__ uint32_t slot_count(const tb_count_view &T, unsigned long long word, uint64_t slot)
+{
+    return T.count_shift ? (uint32_t)(word >> T.count_shift) : T.counts[slot];
 }
 
 __device__ __forceinline__ int64_t read_index_of(const int64_t *__restrict__ offsets, int64_t n_reads, int64_t x)
@@ -70,20 +87,39 @@ k_count_windows(const uint64_t *__restrict__ F, const uint32_t *__restrict__ V, 
             n_counted++;
             uint64_t slot = count_slot_of(key, T.n_slots);
             bool done = false;
-            for (uint64_t probe = 0; probe < T.n_slots && !done; probe++) {
-                unsigned long long cur = T.keys[slot];
-                if (cur == TB_EMPTY) {
-                    cur = atomicCAS(&T.keys[slot], TB_EMPTY, (unsigned long long)key);
+            if (T.count_shift) {
+                const unsigned long long one = 1ull << T.count_shift;
+                for (uint64_t probe = 0; probe < T.n_slots && !done; probe++) {
+                    unsigned long long cur = T.keys[slot];
                     if (cur == TB_EMPTY) {
-                        n_new++;
-                        cur = key;
+                        cur = atomicCAS(&T.keys[slot], TB_EMPTY, (unsigned long long)key | one);
+                        if (cur == TB_EMPTY) {
+                            n_new++;
+                            done = true;
+                        }
                     }
+                    if (!done && (cur & kmask) == key) {
+                        if ((cur >> T.count_shift) < TB_COUNT_PACKED_SATURATE) atomicAdd(&T.keys[slot], one);
+                        done = true;
+                    }
+                    slot = slot + 1 == T.n_slots ? 0 : slot + 1;
                 }
-                if (cur == key) {
-                    atomicAdd(&T.counts[slot], 1u);
-                    done = true;
+            } else {
+                for (uint64_t probe = 0; probe < T.n_slots && !done; probe++) {
+                    unsigned long long cur = T.keys[slot];
+                    if (cur == TB_EMPTY) {
+                        cur = atomicCAS(&T.keys[slot], TB_EMPTY, (unsigned long long)key);
+                        if (cur == TB_EMPTY) {
+                            n_new++;
+                            cur = key;
+                        }
+                    }
+                    if (cur == key) {
+                        atomicAdd(&T.counts[slot], 1u);
+                        done = true;
+                    }
+                    slot = slot + 1 == T.n_slots ? 0 : slot + 1;
                 }
-                slot = slot + 1 == T.n_slots ? 0 : slot + 1;
             }
             if (!done) overflow = 1;
         }
@@ -107,8 +143,9 @@ k_count_histogram(tb_count_view T, unsigned long long *hist, int n_bins)
     for (int i = threadIdx.x; i < n_bins; i += blockDim.x) local[i] = 0;
     __syncthreads();
     for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < T.n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
-        if (T.keys[s] == TB_EMPTY) continue;
-        const uint32_t c = T.counts[s];
+        const unsigned long long word = T.keys[s];
+        if (word == TB_EMPTY) continue;
+        const uint32_t c = slot_count(T, word, s);
         atomicAdd(&local[c < (uint32_t)n_bins ? c : (uint32_t)n_bins - 1], 1u);
     }
     __syncthreads();
@@ -121,8 +158,8 @@ __device__ __forceinline__ uint32_t count_lookup(const tb_count_view &T, uint64_
     uint64_t slot = count_slot_of(key, T.n_slots);
     for (uint64_t probe = 0; probe < T.n_slots; probe++) {
         const unsigned long long cur = T.keys[slot];
-        if (cur == key) return T.counts[slot];
         if (cur == TB_EMPTY) return 0;
+        if (slot_key(T, cur) == key) return slot_count(T, cur, slot);
         slot = slot + 1 == T.n_slots ? 0 : slot + 1;
     }
     return 0;
@@ -135,9 +172,10 @@ k_count_select(tb_count_view A, tb_count_view B, uint32_t min_count, uint32_t ma
                uint32_t counter_max, unsigned long long *out, unsigned long long cap, unsigned long long *n_out)
 {
     for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < A.n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
-        const unsigned long long key = A.keys[s];
-        if (key == TB_EMPTY) continue;
-        uint32_t c = A.counts[s];
+        const unsigned long long word = A.keys[s];
+        if (word == TB_EMPTY) continue;
+        const unsigned long long key = slot_key(A, word);
+        uint32_t c = slot_count(A, word, s);
         if (c < db_min) continue;
         if (c > counter_max) c = counter_max;
         if (c < min_count || c > max_count) continue;

@@ -69,10 +69,17 @@ struct tb_batch_view {
 // ---- k-mer counting (kmer_count.cu) --------------------------------------------------------
 struct tb_count_view {
     unsigned long long *keys;  // canonical k-mers, MSB-first, empty = ~0
-    uint32_t *counts;
+    uint32_t *counts;          // null in the packed layout
     uint64_t n_slots;
     uint32_t part, n_parts;    // only keys of partition `part` of `n_parts` are counted
+    uint32_t count_shift;      // packed layout (k <= TB_COUNT_PACKED_MAX_K): the count lives in the slot's
+                               // word above the key's 2k bits; 0 = separate counts[]
 };
+// The packed layout needs room for a count that saturates far above every cut-off a reader applies:
+// 64 - 2k >= 20 bits.  The saturation test is not atomic with the add, so the field must also absorb
+// one add from every thread that can be in flight (< 2^19 on this part) beyond the threshold.
+#define TB_COUNT_PACKED_MAX_K 22
+#define TB_COUNT_PACKED_SATURATE (1ull << 19)
 // stats[0] += windows counted, stats[1] += new distinct keys, stats[2] |= table full
 cudaError_t tb_launch_count_windows(const uint64_t *d_F, const uint32_t *d_V, const int64_t *d_offsets, int64_t n_reads,
                                     int64_t total_bases, int k, tb_count_view T, unsigned long long *d_stats,

@@ -154,11 +154,11 @@ def write_kmers(path: str, keys: np.ndarray, k: int, chunk: int = 1 << 22) -> in
     return len(keys)
 
 
-def _table_slots(table_gb: float) -> int:
+def _table_slots(table_gb: float, k: int) -> int:
     if table_gb <= 0:
         free = kmers.device_info(kmers.lib.tb_get_device())["hbm_bytes"]
         table_gb = free / 4 / 1e9
-    return max(1 << 16, int(table_gb * 1e9 / 12))
+    return max(1 << 16, int(table_gb * 1e9 / kmers.lib.tb_counter_slot_bytes(k)))
 
 
 def _count_pair(files_a, files_b, k, n_slots, part, n_parts, threads):
@@ -220,7 +220,7 @@ def find_unique_kmers(files_a: List[str], files_b: List[str], k: int, table_gb: 
     """The whole computation.  Returns (keys_a_only, keys_b_only, (min_a, max_a), (min_b, max_b)) with
     sorted MSB-first canonical keys.  Libraries with more distinct k-mers than one table holds are
     counted in 2, 4, ... partitions (passes over the input)."""
-    n_slots = _table_slots(table_gb)
+    n_slots = _table_slots(table_gb, k)
     while True:
         try:
             return _run(files_a, files_b, k, n_slots, n_parts, threads, cutoffs, scratch_dir)

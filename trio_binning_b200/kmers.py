@@ -205,6 +205,8 @@ lib.tb_route_fastx.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_int, C.c_i
                                C.POINTER(StreamStats)]
 lib.tb_counter_create.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int]
 lib.tb_counter_create.restype = C.c_void_p
+lib.tb_counter_slot_bytes.argtypes = [C.c_int]
+lib.tb_counter_slot_bytes.restype = C.c_int
 lib.tb_counter_destroy.argtypes = [C.c_void_p]
 lib.tb_counter_destroy.restype = None
 lib.tb_counter_add_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
