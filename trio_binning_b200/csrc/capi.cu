@@ -111,10 +111,13 @@ int use_device(int device)
 
 // m of the minimizer scheme (same rule as tb_minimizer_m in classify.cu; checked by a test that
 // compares bitmap sizes, and by every parity test: build and look-up share the device function)
+#ifndef TB_MINI_W
+#define TB_MINI_W 7
+#endif
 int tb_minimizer_m_host(int k)
 {
     if (k >= 22) return 16;
-    int m = k - 6;
+    int m = k - (TB_MINI_W - 1);
     const int floor13 = k - 2 < 13 ? k - 2 : 13;
     if (m < floor13) m = floor13;
     const int half = (k + 1) / 2;

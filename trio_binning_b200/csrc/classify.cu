@@ -683,10 +683,13 @@ k_pair_filter_build(const unsigned long long *__restrict__ slots, uint64_t n_slo
 // windows pass it (measured at k = 15 .. 17 with m = k - 6: profiles/r2_ksweep_before_m13.jsonl)
 // -- and never less than k/2, so that the first and the last m-mer of a k-mer together cover all
 // of its bases (their hashes also address the word and the bits)
+#ifndef TB_MINI_W
+#define TB_MINI_W 7   // m-mers per window below k = 22 (measurement knob; capi.cu has the same default)
+#endif
 __host__ __device__ constexpr int tb_minimizer_m(int k)
 {
     if (k >= 22) return 16;
-    int m = k - 6;
+    int m = k - (TB_MINI_W - 1);
     const int floor13 = k - 2 < 13 ? k - 2 : 13;
     if (m < floor13) m = floor13;
     const int half = (k + 1) / 2;
