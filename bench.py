@@ -631,6 +631,10 @@ def run_gpu_arm(args, rank, local_rank, world):
     dist.barrier()
     few = max(3, args.steps // 5)
     e2e_hostpack_ms = dist.reduce(packed_pass(few, True), "MAX") * args.steps / few
+    # ---- what the box can feed its GPUs with: plain pinned -> device copies, all ranks at once
+    dist.barrier()
+    h2d_gbs = kmers.h2d_bench(256 << 20, 60)
+    h2d_sum, h2d_min = dist.reduce(h2d_gbs, "SUM"), dist.reduce(h2d_gbs, "MIN")
     # ---- HBM-resident, ASCII form (k_pack on the device is part of the step)
     clf.submit(0, None, None, n_reads=n_reads)
     clf.wait(0)
@@ -743,6 +747,12 @@ def run_gpu_arm(args, rank, local_rank, world):
             "config": workload_config(args, wl, world),
             "e2e": dict(e2e_variants["packed"], route="packed", clocks=clocks_e2e),
             "e2e_variants": e2e_variants,
+            "h2d_ceiling": {
+                "aggregate_gb_per_s": h2d_sum, "slowest_rank_gb_per_s": h2d_min,
+                "e2e_h2d_gb_per_s": rate(e2e_packed_ms) * pbs[0].h2d_bytes / total / 1e9,
+                "what": "plain cudaMemcpyAsync of a 256 MB page-locked buffer, 60 times, by every rank at the same time "
+                        "(tb_h2d_bench), summed over ranks; beside it the host-to-device bytes per second the e2e "
+                        "figure moves -- at N = 8 the two meet: the host side of the box, not the GPUs, bounds e2e"},
             "host_pack": {"value": total / pack_s, "unit": UNIT, "threads": host_threads,
                           "what": "tb_pack_reads (AVX-512/AVX2, multi-threaded): ASCII -> 2-bit pinned batch, this rank, mean of 5 calls"},
             "gpu_launches": 5 * args.steps,

@@ -359,6 +359,10 @@ int tb_classifier_stats(tb_classifier *c, int slot, uint64_t *n_windows,
 int tb_gather_bench(uint64_t table_bytes, int loads_in_flight, int threads_per_block,
                     int blocks_per_sm, int steps, int variant,
                     double *sectors_per_s, float *ms);
+/* Plain host-to-device copies of a page-locked buffer on the current device, `iters` of `bytes`
+ * each, timed with events (GB/s).  Measurement aid: run by all ranks of bench.py at once it gives
+ * the aggregate the box can feed its GPUs with, the ceiling of the end-to-end figure at N > 1. */
+int tb_h2d_bench(uint64_t bytes, int iters, double *gb_per_s);
 
 #ifdef __cplusplus
 }

@@ -884,3 +884,12 @@ def test_two_level_bitmap_addressing(kmers, oracle, k):
     oracle.set_free(ob)
     kmers.destroy_kmer_hash_set(A)
     kmers.destroy_kmer_hash_set(B)
+
+
+@pytest.mark.gpu
+def test_measurement_aids_run(kmers):
+    """bench.py's denominators come from the library itself: the random-sector gather and the plain
+    host-to-device copy.  Smoke only: they run and report a plausible rate."""
+    rate, ms = kmers.gather_bench(64 << 20, 8, 256, 8, 8, 0)
+    assert rate > 1e9 and ms > 0
+    assert kmers.h2d_bench(16 << 20, 8) > 1.0   # GB/s

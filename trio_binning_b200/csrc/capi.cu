@@ -1304,4 +1304,38 @@ int tb_gather_bench(uint64_t table_bytes, int loads_in_flight, int threads_per_b
     return 0;
 }
 
+int tb_h2d_bench(uint64_t bytes, int iters, double *gb_per_s)
+{
+    if (use_device(g_device)) return -1;
+    if (bytes == 0 || iters < 1) return fail("tb_h2d_bench: nothing to copy");
+    void *host = nullptr, *dev = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaHostAlloc(&host, bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&dev, bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) {
+        memset(host, 0x5A, bytes);  // first touch on this thread's NUMA node
+        for (int i = 0; i < std::max(2, iters / 10) && e == cudaSuccess; i++)
+            e = cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = cudaEventRecord(e0, stream);
+    for (int i = 0; i < iters && e == cudaSuccess; i++) e = cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    float t = 0;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, e0, e1);
+    if (e == cudaSuccess && gb_per_s) *gb_per_s = (double)bytes * iters / (t * 1e-3) / 1e9;
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (stream) cudaStreamDestroy(stream);
+    if (dev) cudaFree(dev);
+    if (host) cudaFreeHost(host);
+    if (e != cudaSuccess) return fail("tb_h2d_bench: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 }  // extern "C"

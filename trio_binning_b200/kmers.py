@@ -146,6 +146,7 @@ lib.tb_classifier_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), 
                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
 lib.tb_gather_bench.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.POINTER(C.c_double), C.POINTER(C.c_float)]
+lib.tb_h2d_bench.argtypes = [C.c_uint64, C.c_int, C.POINTER(C.c_double)]
 
 
 class _PackedBatch(C.Structure):
@@ -910,6 +911,13 @@ def crc32(data: bytes, crc: int = 0) -> int:
 
 def crc32_accelerated() -> bool:
     return bool(lib.tb_crc32_accelerated())
+
+
+def h2d_bench(n_bytes: int = 256 << 20, iters: int = 100) -> float:
+    """GB/s of plain pinned-host -> device copies on the current device (tb_h2d_bench)."""
+    rate = C.c_double()
+    _check(lib.tb_h2d_bench(n_bytes, iters, C.byref(rate)))
+    return rate.value
 
 
 def gather_bench(table_bytes: int, loads_in_flight: int = 8, threads_per_block: int = 256,
