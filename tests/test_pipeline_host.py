@@ -201,3 +201,17 @@ def test_plain_writer_random_shapes_against_cpython(kmers, seq, tmp_path):
         for name in os.listdir(want_dir):
             assert _content(os.path.join(got_dir, name), False) == _content(os.path.join(want_dir, name), False), (trial, name, bins)
         assert got_tsv == want_tsv
+
+
+@pytest.mark.parametrize("gz_out", [True, False])
+def test_a_full_disk_is_an_error_with_its_reason(kmers, tmp_path, gz_out):
+    """write() failing on an output file (ENOSPC on /dev/full) must end the run with an error that
+    names the reason -- never a silently short output."""
+    if not os.path.exists("/dev/full"):
+        pytest.skip("no /dev/full")
+    reads = str(tmp_path / "reads.fastq")
+    _fastx(reads, [20_000] * 40, seed=1)
+    with open(tmp_path / "out.tsv", "wb") as t:
+        with pytest.raises(RuntimeError, match="No space left"):
+            kmers.route_fastx_file(reads, "AB", "/dev/full", str(tmp_path / "b"), str(tmp_path / "u"), tsv_fd=t.fileno(),
+                                   gzip_output=gz_out, batch_bases=100_000)

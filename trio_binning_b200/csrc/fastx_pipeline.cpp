@@ -885,6 +885,7 @@ struct BinWriter {
     virtual void finish() = 0;
     uint64_t raw_bytes = 0, out_bytes = 0;
     bool failed = false;
+    int fail_errno = 0;
 };
 
 struct GzFileWriter : BinWriter {
@@ -955,7 +956,8 @@ struct GzFileWriter : BinWriter {
             size_t off = 0;
             while (off < out->size()) {
                 ssize_t w = ::write(fd, out->data() + off, out->size() - off);
-                if (w <= 0) { failed = true; break; }
+                if (w < 0 && errno == EINTR) continue;
+                if (w <= 0) { failed = true; fail_errno = errno; break; }
                 off += (size_t)w;
             }
             out_bytes += out->size();
@@ -970,7 +972,7 @@ struct GzFileWriter : BinWriter {
             pending.clear();
         }
         drain(true);
-        if (fd >= 0) ::close(fd);
+        if (fd >= 0 && ::close(fd) != 0) { failed = true; fail_errno = errno; }  // deferred write errors (quota, NFS) surface here
         fd = -1;
     }
 };
@@ -1021,7 +1023,7 @@ struct PyTextFileWriter : BinWriter {
         while (n > 0) {
             const ssize_t w = ::write(fd, p, n);
             if (w < 0 && errno == EINTR) continue;
-            if (w <= 0) { failed = true; return; }
+            if (w <= 0) { failed = true; fail_errno = errno; return; }
             p += w;
             n -= (size_t)w;
         }
@@ -1080,7 +1082,7 @@ struct PyTextFileWriter : BinWriter {
     {
         text_flush();
         buffer_flush();
-        if (fd >= 0) ::close(fd);
+        if (fd >= 0 && ::close(fd) != 0) { failed = true; fail_errno = errno; }
         fd = -1;
     }
 };
@@ -1490,6 +1492,7 @@ int run_pipeline(const PipelineConfig &cfg, tb_stream_stats *stats)
         wa->drain(false);
         wb->drain(false);
         wu->drain(false);
+        if (wa->failed || wb->failed || wu->failed) set_rc(-9);  // disk full, quota: stop reading, do not classify on
         write_s += seconds_since(t0);
         n_batches_done++;
     };
@@ -1521,7 +1524,12 @@ int run_pipeline(const PipelineConfig &cfg, tb_stream_stats *stats)
     wu->finish();
     write_s += seconds_since(t_fin);
     int out_rc = rc.load();
-    if (wa->failed || wb->failed || wu->failed) out_rc = out_rc ? out_rc : -9;
+    if (wa->failed || wb->failed || wu->failed) {
+        const int e = wa->fail_errno ? wa->fail_errno : (wb->fail_errno ? wb->fail_errno : wu->fail_errno);
+        const std::string why = std::string("writing an output file failed: ") + (e ? strerror(e) : "compression error");
+        set_err(why.c_str());
+        out_rc = out_rc ? out_rc : -9;
+    }
     if (!err_text.empty()) {
         fprintf(stderr, "tb_classify_fastx: %s\n", err_text.c_str());
         tb_internal_set_error(err_text.c_str());
