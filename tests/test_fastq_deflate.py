@@ -66,6 +66,13 @@ def test_fasta_and_odd_shapes(kmers):
     _check(kmers, lower)
     crlf = _fastq(5, 30_000, 5).replace(b"\n", b"\r\n")
     _check(kmers, crlf)
+    # Fibonacci frequencies: the unrestricted Huffman tree is ~25 deep, the code must be cut to 14 bits
+    fib = [1, 2]
+    while sum(fib) < 200_000:
+        fib.append(fib[-1] + fib[-2])
+    skewed = np.concatenate([np.full(f, 40 + i, dtype=np.uint8) for i, f in enumerate(fib)])
+    rng.shuffle(skewed)
+    _check(kmers, skewed.tobytes() + b"\n")
 
 
 def test_reference_fixture_reads(kmers):

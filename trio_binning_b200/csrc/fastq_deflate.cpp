@@ -17,6 +17,8 @@ namespace {
 constexpr size_t kMinBlock = 2048;         // do not open a new block for less text than this
 constexpr size_t kMaxBlock = 256u << 10;   // nor let one grow beyond this (keeps the codes local)
 constexpr size_t kLongLine = 64;           // lines at least this long decide the class of a block
+constexpr int kMaxLitBits = 14;            // literal/length code lengths: four literals fit one 56-bit put
+constexpr int kPairSymbols = 128;          // byte-pair table for blocks with at most this many distinct bytes
 
 const uint16_t LEN_BASE[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59,
                                 67, 83, 99, 115, 131, 163, 195, 227, 258 };
@@ -111,49 +113,36 @@ void canonical_codes(const uint8_t *lens, int n, uint16_t *codes)
     }
 }
 
+// LSB-first bit writer.  Invariant between calls: fewer than 8 bits are pending, so a call may add
+// up to 56 bits before it stores -- one unaligned 8-byte store, of which only the whole bytes count.
 struct BitWriter {
-    unsigned char *p, *end;
+    unsigned char *p, *end;  // an 8-byte store at p is inside the buffer while p <= end
     uint64_t acc = 0;
     unsigned n = 0;
     bool overflow = false;
-    inline void put(uint32_t bits, unsigned len)
+    inline void flush()
     {
-        acc |= (uint64_t)bits << n;
-        n += len;
-        if (n >= 32) {
-            if (end - p < 4) { overflow = true; n -= 32; acc >>= 32; return; }
-            const uint32_t w = (uint32_t)acc;
-            memcpy(p, &w, 4);  // little-endian hosts
-            p += 4;
-            acc >>= 32;
-            n -= 32;
-        }
+        if (p > end) { overflow = true; acc = 0; n = 0; return; }
+        memcpy(p, &acc, 8);  // little-endian hosts
+        p += n >> 3;
+        acc >>= n & 56u;
+        n &= 7u;
     }
-    inline void put2(uint32_t a, unsigned la, uint32_t b, unsigned lb)
+    // len <= 56
+    inline void put(uint64_t bits, unsigned len)
     {
-        // n < 32 on entry, la + lb <= 30: everything fits into the 64-bit accumulator
-        acc |= (uint64_t)a << n;
-        n += la;
-        acc |= (uint64_t)b << n;
-        n += lb;
-        if (n >= 32) {
-            if (end - p < 4) { overflow = true; n -= 32; acc >>= 32; return; }
-            const uint32_t w = (uint32_t)acc;
-            memcpy(p, &w, 4);
-            p += 4;
-            acc >>= 32;
-            n -= 32;
-        }
+        acc |= bits << n;
+        n += len;
+        flush();
     }
     void finish_byte()
     {
-        while (n > 0) {
-            if (p == end) { overflow = true; return; }
+        if (n > 0) {
+            if (p > end) { overflow = true; return; }
             *p++ = (unsigned char)acc;
-            acc >>= 8;
-            n = n > 8 ? n - 8 : 0;
         }
         acc = 0;
+        n = 0;
     }
 };
 
@@ -206,7 +195,7 @@ bool encode_block(const unsigned char *d, size_t n, bool final_block, BitWriter 
     for (int s = 0; s < 256; s++) freq[s] += f1[s] + f2[s] + f3[s];
     freq[256] = 1;
     uint8_t ll[286], dl[1] = { 1 };  // one distance code (distance 1) of one bit, used or not
-    huffman_lengths(freq, 286, 15, ll);
+    huffman_lengths(freq, 286, kMaxLitBits, ll);
     uint16_t lcodes[286];
     canonical_codes(ll, 286, lcodes);
     int hlit = 286;
@@ -256,23 +245,56 @@ bool encode_block(const unsigned char *d, size_t n, bool final_block, BitWriter 
         bw.put(cl_code[cls[i].sym], cl_len[cls[i].sym]);
         if (cls[i].extra_bits) bw.put(cls[i].extra_val, cls[i].extra_bits);
     }
-    // the text
-    uint32_t lit_code[256];  // code | length << 16
-    for (int s = 0; s < 256; s++) lit_code[s] = lcodes[s] | ((uint32_t)ll[s] << 16);
+    // the text: literals go out two at a time through a table of byte PAIRS (code and length of both,
+    // merged), four pairs per eight bytes and two stores.  Only pairs of symbols that occur in the
+    // block are filled in -- a few dozen symbols for any kind of FASTA/FASTQ line; text with more
+    // distinct bytes than kPairSymbols takes the one-literal path.
+    uint8_t used[256];
+    int n_used = 0;
+    for (int s = 0; s < 256; s++)
+        if (ll[s]) used[n_used++] = (uint8_t)s;
+    // indexed by the two bytes as one little-endian 16-bit number (a dense index was tried: its
+    // multiply costs more than the spread-out rows do)
+    static thread_local std::vector<uint64_t> pair_store;
+    const bool pairs = n_used <= kPairSymbols && (size_t)n_used * n_used <= 2 * n;  // filling it must not cost more than using it
+    if (pairs) {
+        if (pair_store.empty()) pair_store.resize(65536);
+        for (int a = 0; a < n_used; a++) {
+            const unsigned sa = used[a], la = ll[sa];
+            const uint64_t ca = lcodes[sa];
+            for (int b = 0; b < n_used; b++) {
+                const unsigned sb = used[b];
+                pair_store[sa | (sb << 8)] =
+                    (ca | ((uint64_t)lcodes[sb] << la)) | ((uint64_t)(la + ll[sb]) << 32);
+            }
+        }
+    }
+    const uint64_t *pair = pair_store.data();
+    auto pair_of = [&](const unsigned char *q) {
+        uint16_t i;
+        memcpy(&i, q, 2);
+        return pair[i];
+    };
+    auto one = [&](unsigned char c) { bw.put(lcodes[c], ll[c]); };
     tokenize(d, n,
              [&](const unsigned char *q) {
-                 // two codes (<= 30 bits) per flush check
-                 for (int t = 0; t < 8; t += 2) {
-                     const uint32_t a = lit_code[q[t]], b = lit_code[q[t + 1]];
-                     bw.put2(a & 0xFFFF, a >> 16, b & 0xFFFF, b >> 16);
+                 if (!pairs) {
+                     for (int t = 0; t < 8; t++) one(q[t]);
+                     return;
                  }
+                 const uint64_t e0 = pair_of(q), e1 = pair_of(q + 2), e2 = pair_of(q + 4), e3 = pair_of(q + 6);
+                 const unsigned l0 = (unsigned)(e0 >> 32), l1 = (unsigned)(e1 >> 32), l2 = (unsigned)(e2 >> 32),
+                                l3 = (unsigned)(e3 >> 32);
+                 // two pairs are at most 4 * kMaxLitBits = 56 bits
+                 bw.put((e0 & 0xFFFFFFFFull) | ((e1 & 0xFFFFFFFFull) << l0), l0 + l1);
+                 bw.put((e2 & 0xFFFFFFFFull) | ((e3 & 0xFFFFFFFFull) << l2), l2 + l3);
              },
-             [&](unsigned char c) { bw.put(lcodes[c], ll[c]); },
+             one,
              [&](unsigned len) {
                  const unsigned s = 257 + lc.sym[len];
-                 bw.put(lcodes[s], ll[s]);
-                 if (lc.extra_bits[len]) bw.put(lc.extra_val[len], lc.extra_bits[len]);
-                 bw.put(0, 1);  // the one distance code: distance 1
+                 // length code, its extra bits, and the one distance code (one bit): <= 14 + 5 + 1
+                 const unsigned eb = lc.extra_bits[len];
+                 bw.put((uint64_t)lcodes[s] | ((uint64_t)lc.extra_val[len] << ll[s]), ll[s] + eb + 1);
              });
     bw.put(lcodes[256], ll[256]);
     return !bw.overflow;
@@ -309,7 +331,7 @@ bool fastq_gzip_member(const char *data, size_t n, std::string &out, bool verify
     memcpy(base, head, 10);
     BitWriter bw;
     bw.p = base + 10;
-    bw.end = base + (out.size() - start) - 8;
+    bw.end = base + (out.size() - start) - 24;  // room for the last store, the final byte and the trailer
 
     // blocks: cut where the class of (long) lines changes, or when a block is full
     size_t block_start = 0, pos = 0;
