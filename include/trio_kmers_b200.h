@@ -248,6 +248,11 @@ int tb_float_repr(double x, char *buf, int buf_len);
  * followed by the bytes, length -1 for "no quality" (testing aid; no GPU involved).  Returns the number of records, or < 0: -1 cannot
  * open, -2 unreadable input (corrupt gzip data; message in tb_last_error), -3 out of memory. */
 int64_t tb_fastx_dump(const char *reads_path, int out_fd);
+/* The lines of a FASTA/FASTQ(.gz) file as the native reader's input stage delivers them (gzip,
+ * BGZF or one gzip stream decoded on `decode_threads` cores; line ends translated to '\n'),
+ * written to out_fd (testing aid).  Returns the number of bytes, -1 cannot open, -2 unreadable
+ * input (message in tb_last_error), -3 write error. */
+int64_t tb_fastx_cat(const char *reads_path, int out_fd, int decode_threads);
 /* Decode a gzip file with the pipeline's own streaming inflate, `chunk` bytes per read call,
  * and write the result to out_fd (testing aid; no GPU involved).  File semantics are those of
  * Python's gzip module: members concatenated, zero padding after a member skipped, anything

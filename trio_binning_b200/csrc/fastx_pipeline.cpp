@@ -30,6 +30,7 @@
 #include "fastq_deflate.h"
 #include "gz_stream.h"
 
+#include <sys/mman.h>
 #include <sys/stat.h>
 
 #include <algorithm>
@@ -66,6 +67,9 @@ class LineSource {
 public:
     // host threads that may decode in parallel (BGZF input only); call before the first next()
     void set_threads(int n) { decode_threads_ = n < 1 ? 1 : (n > 8 ? 8 : n); }
+    // ... and for ONE plain gzip stream cut into spans: its decoder is slower per core than the
+    // serial one, so it gets more of them
+    void set_gzip_threads(int n) { gzip_threads_ = n < 2 ? 2 : (n > 12 ? 12 : n); }
     bool open(const char *path, std::string &err)
     {
         const size_t n = strlen(path);
@@ -77,6 +81,21 @@ public:
             const ssize_t got = ::pread(fd_, head, sizeof head, 0);
             size_t total = 0;
             bgzf_ = got >= 18 && bgzf_block_size(head, (size_t)got, total);
+            // a plain gzip stream in a regular file that is worth it: decoded on several cores
+            // (TB_PGZIP=0 turns that off; TB_PGZIP_SPAN / TB_PGZIP_MIN: span and smallest file, bytes)
+            const char *on = getenv("TB_PGZIP"), *span = getenv("TB_PGZIP_SPAN"), *least = getenv("TB_PGZIP_MIN");
+            if (span && atoll(span) >= 1024) span_bytes_ = (uint64_t)atoll(span);
+            const uint64_t min_size = least ? (uint64_t)atoll(least) : 16 * span_bytes_;
+            struct stat st;
+            if (!bgzf_ && !(on && on[0] == '0') && fstat(fd_, &st) == 0 && S_ISREG(st.st_mode) && (uint64_t)st.st_size >= min_size &&
+                st.st_size > 64) {
+                void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd_, 0);
+                if (m != MAP_FAILED) {
+                    map_ = (const unsigned char *)m;
+                    map_size_ = (uint64_t)st.st_size;
+                    pgzip_ok_ = true;
+                }
+            }
         }
         return true;
     }
@@ -89,6 +108,7 @@ public:
         cv_.notify_all();
         if (producer_.joinable()) producer_.join();
         for (auto &w : workers_) w.join();
+        if (map_) munmap((void *)map_, (size_t)map_size_);
         if (fd_ >= 0) ::close(fd_);
     }
     // Next line INCLUDING its terminator translated to '\n' (absent only at end of input), as a
@@ -227,6 +247,11 @@ private:
         }
         return std::make_shared<Chunk>();
     }
+    void free_chunk(const ChunkPtr &c)
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        free_.push_back(c);
+    }
     // append to the ordered queue (blocks while too many chunks are in flight); false = stopping
     bool enqueue(const ChunkPtr &c, bool as_work)
     {
@@ -254,9 +279,9 @@ private:
     }
 
     // serial stream: the producer thread decodes (or reads) chunk after chunk
-    void produce_serial(bool continue_on_fd)
+    void produce_serial(bool continue_on_fd, bool already_open = false)
     {
-        if (gz_) {
+        if (gz_ && !already_open) {
             gzs_.open_fd(fd_, !continue_on_fd);
         }
         for (;;) {
@@ -395,10 +420,258 @@ private:
         }
     }
 
+    // ---- one plain gzip stream on several cores (gz_stream.h: SpanInflate) ----------------------
+    // The file is cut into spans of span_bytes_ compressed bytes.  Workers decode spans side by side,
+    // each from the first block header it can verify, into 16-bit symbols with markers for the text
+    // before the span.  This thread takes the results in file order: a span counts only if it starts
+    // at the bit where its predecessor stopped (else it is decoded again from there, now knowing
+    // where), its markers are resolved against the 32 KiB before it, members' CRC-32 and ISIZE are
+    // checked, and the text goes to the parser.  Whatever is not a member followed by another member
+    // (padding, garbage, the end) is left to the serial reader, and so is any failure: it decodes
+    // the current member again from its start, skips what was delivered, and reports -- or, should
+    // the failure have been this code's, simply carries on.
+    struct SpanJob {
+        uint64_t start_bit = 0, end_bit = 0;
+        bool search = false;
+        bool done = false, taken = false;
+        tb::SpanResult res;
+    };
+    bool parallel_gzip() const { return gz_ && !bgzf_ && pgzip_ok_; }
+
+    void work_spans()
+    {
+        tb::SpanInflate inflate;
+        for (;;) {
+            SpanJob *job = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || spans_closed_ || !span_work_.empty(); });
+                if (stop_ || (span_work_.empty() && spans_closed_)) return;
+                job = span_work_.front();
+                span_work_.pop_front();
+                job->taken = true;
+            }
+            const auto t0 = Clock::now();
+            try {
+                inflate.decode(map_, map_size_, job->start_bit, job->search, job->end_bit, !job->search, job->res);
+            } catch (const std::exception &) {
+                job->res.found = false;
+                job->res.error = "out of memory while decoding";
+            }
+            inflate_ns_.fetch_add((uint64_t)(seconds_since(t0) * 1e9));
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                job->done = true;
+            }
+            cv_.notify_all();
+        }
+    }
+
+    void close_spans()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            spans_closed_ = true;
+            span_work_.clear();
+        }
+        cv_.notify_all();
+    }
+
+    // the serial reader takes the current member again from its start and skips what was delivered
+    void pgzip_fallback(uint64_t member_start, uint64_t delivered)
+    {
+        close_spans();
+        if (::lseek(fd_, (off_t)member_start, SEEK_SET) < 0) {
+            push_end(true, "cannot seek in the reads file");
+            return;
+        }
+        bgzf_bytes_ = member_start;
+        gzs_.open_fd(fd_, member_start == 0);
+        std::vector<char> skip(1u << 20);
+        while (delivered > 0) {
+            const long got = gzs_.read(skip.data(), (size_t)std::min<uint64_t>(delivered, skip.size()));
+            if (got <= 0) {
+                push_end(true, got < 0 ? "corrupt gzip input: " + gzs_.error() : std::string("corrupt gzip input: stream ends early"));
+                return;
+            }
+            delivered -= (uint64_t)got;
+        }
+        produce_serial(true, true);
+    }
+
+    void produce_pgzip()
+    {
+        const unsigned char *file = map_;
+        const uint64_t size = map_size_;
+        constexpr size_t W = tb::SpanResult::kWindow;
+        const size_t hdr = tb::SpanInflate::member_header_length(file, (size_t)std::min<uint64_t>(size, 1u << 20));
+        if (hdr == 0) {  // whatever this is, the serial reader says it
+            close_spans();
+            produce_serial(false);
+            return;
+        }
+        const uint64_t S = span_bytes_;
+        const uint64_t n_spans = (size - hdr + S - 1) / S;
+        const size_t ahead = 2 * (size_t)gzip_threads_ + 1;
+        auto &ring = span_ring_;  // a member: workers may still be writing into a job when this function returns
+        for (size_t i = 0; i < ahead; i++) ring.emplace_back(new SpanJob());
+        auto issue = [&](uint64_t k) {
+            SpanJob *j = ring[k % ahead].get();
+            j->search = k > 0;
+            j->start_bit = (hdr + k * S) * 8;
+            j->end_bit = (hdr + (k + 1) * S) * 8;
+            j->done = j->taken = false;
+            std::lock_guard<std::mutex> lk(m_);
+            span_work_.push_back(j);
+        };
+        uint64_t issued = 0;
+        std::vector<unsigned char> window(W, 0);
+        uint64_t expected = hdr * 8;      // where the next span must start
+        bool expected_fresh = true;
+        uint64_t member_start = 0, member_delivered = 0, member_len = 0;
+        uint32_t crc = 0;
+        int bad_streak = 0;
+        bool speculate = true;
+        uint64_t n_accepted = 0, n_redone = 0, n_covered = 0;
+        const bool debug = getenv("TB_PGZIP_DEBUG") != nullptr;
+        auto report = [&](const char *how) {
+            if (debug)
+                fprintf(stderr, "pgzip: %llu spans of %llu bytes on %d threads: %llu as guessed, %llu decoded again, %llu covered "
+                        "by a predecessor; %s\n", (unsigned long long)n_spans, (unsigned long long)S, gzip_threads_,
+                        (unsigned long long)n_accepted, (unsigned long long)n_redone, (unsigned long long)n_covered, how);
+        };
+        tb::SpanInflate own;               // for spans that have to be decoded again, in order
+        tb::SpanResult own_res;
+
+        for (uint64_t k = 0; k < n_spans; k++) {
+            while (speculate && issued < n_spans && issued < k + ahead) issue(issued++);
+            cv_.notify_all();
+            const uint64_t end_bit = (hdr + (k + 1) * S) * 8;
+            if (expected >= end_bit && k + 1 < n_spans) {
+                // the predecessor's last block reached past this whole span
+                if (speculate) {
+                    std::unique_lock<std::mutex> lk(m_);
+                    SpanJob *j = ring[k % ahead].get();
+                    cv_.wait(lk, [&] { return stop_ || j->done; });
+                    if (stop_) return;
+                }
+                n_covered++;
+                continue;
+            }
+            tb::SpanResult *res = nullptr;
+            if (speculate) {
+                SpanJob *j = ring[k % ahead].get();
+                {
+                    std::unique_lock<std::mutex> lk(m_);
+                    cv_.wait(lk, [&] { return stop_ || j->done; });
+                    if (stop_) return;
+                }
+                if (k == 0 || (j->res.found && j->res.start_bit == expected)) {
+                    res = &j->res;
+                    bad_streak = 0;
+                    n_accepted++;
+                } else if (++bad_streak >= 3) {
+                    // no dynamic blocks to be found (stored data?) or a format this search does not
+                    // see through: stop guessing, decode the rest in order on this thread
+                    speculate = false;
+                    close_spans();
+                }
+            }
+            if (!res) {
+                const auto t0 = Clock::now();
+                try {
+                    own.decode(file, size, expected, false, end_bit, expected_fresh, own_res);
+                } catch (const std::exception &) {
+                    own_res.error = "out of memory while decoding";
+                }
+                inflate_ns_.fetch_add((uint64_t)(seconds_since(t0) * 1e9));
+                res = &own_res;
+                n_redone++;
+            }
+            if (!res->error.empty()) {
+                report(("serial reader takes the member again: " + res->error).c_str());
+                pgzip_fallback(member_start, member_delivered);
+                return;
+            }
+            // ---- markers -> bytes, member by member; CRC-32 and ISIZE as the serial reader checks them
+            const auto t0 = Clock::now();
+            const size_t n = res->n_sym - W;
+            ChunkPtr c = fresh_chunk();
+            bool ok = true;
+            try {
+                c->data.resize(n ? n : 1);
+            } catch (const std::exception &) {
+                ok = false;
+            }
+            unsigned char *out = (unsigned char *)c->data.data();
+            ok = ok && tb::resolve_markers(res->sym.data() + W, n, window.data(), out);
+            size_t from = 0;
+            uint64_t next_member_start = member_start, delivered_after = member_delivered + n;
+            for (size_t e = 0; ok && e < res->ends.size(); e++) {
+                const size_t to = res->ends[e].pos - W;
+                crc = tb::crc32_any(crc, out + from, to - from);
+                member_len += to - from;
+                if (crc != res->ends[e].crc || (uint32_t)member_len != res->ends[e].isize) ok = false;
+                crc = 0;
+                member_len = 0;
+                from = to;
+                next_member_start = res->ends[e].next_off;
+                delivered_after = n - to;
+            }
+            if (!ok) {
+                free_chunk(c);
+                report("serial reader takes the member again: checksum, length or marker out of range");
+                pgzip_fallback(member_start, member_delivered);
+                return;
+            }
+            crc = tb::crc32_any(crc, out + from, n - from);
+            member_len += n - from;
+            member_start = next_member_start;
+            member_delivered = delivered_after;
+            if (n >= W) {
+                memcpy(window.data(), out + n - W, W);
+            } else if (n > 0) {
+                memmove(window.data(), window.data() + n, W - n);
+                memcpy(window.data() + W - n, out, n);
+            }
+            expected = res->stop_bit;
+            expected_fresh = res->stop_fresh;
+            bytes_in_ = expected / 8;
+            inflate_ns_.fetch_add((uint64_t)(seconds_since(t0) * 1e9));
+            if (n > 0) {
+                c->len = n;
+                c->scan_flags();
+                c->done = true;
+                if (!enqueue(c, false)) return;
+            } else {
+                free_chunk(c);
+            }
+            if (res->tail) {
+                // padding, garbage or the end of the file: the serial reader's rules apply
+                close_spans();
+                if (::lseek(fd_, (off_t)res->tail_off, SEEK_SET) < 0) {
+                    push_end(true, "cannot seek in the reads file");
+                    return;
+                }
+                bgzf_bytes_ = res->tail_off;  // compressed bytes before the serial reader's
+                report("last member done, the serial reader looks at what follows");
+                produce_serial(true);
+                return;
+            }
+        }
+        // the spans ran out inside a member: truncated input -- the serial reader reports it
+        report("input ends inside a member: serial reader takes it again");
+        pgzip_fallback(member_start, member_delivered);
+    }
+
     void start()
     {
         started_ = true;
-        if (parallel_bgzf()) {
+        if (parallel_gzip()) {
+            max_in_flight_ = 3;  // spans are tens of megabytes of text each
+            for (int i = 0; i < gzip_threads_; i++) workers_.emplace_back([this] { work_spans(); });
+            producer_ = std::thread([this] { produce_pgzip(); });
+        } else if (parallel_bgzf()) {
             max_in_flight_ = 2 + 2 * (size_t)decode_threads_;
             for (int i = 0; i < decode_threads_; i++) workers_.emplace_back([this] { work(); });
             producer_ = std::thread([this] { produce_bgzf(); });
@@ -447,7 +720,7 @@ private:
     }
 
     bool gz_ = false, bgzf_ = false, eof_ = false, pending_cr_ = false, started_ = false, stop_ = false;
-    int decode_threads_ = 2;
+    int decode_threads_ = 2, gzip_threads_ = 4;
     tb::GzStream gzs_;
     int fd_ = -1;
     std::thread producer_;
@@ -455,6 +728,11 @@ private:
     std::mutex m_;
     std::condition_variable cv_;
     std::deque<ChunkPtr> ordered_, work_;
+    std::deque<SpanJob *> span_work_;
+    std::vector<std::unique_ptr<SpanJob>> span_ring_;
+    bool spans_closed_ = false, pgzip_ok_ = false;
+    const unsigned char *map_ = nullptr;
+    uint64_t map_size_ = 0, span_bytes_ = 2u << 20;
     std::vector<ChunkPtr> free_;
     size_t max_in_flight_ = 3;
     ChunkPtr cur_chunk_;
@@ -1224,6 +1502,7 @@ int run_pipeline(const PipelineConfig &cfg, tb_stream_stats *stats)
     // a quarter of the host threads may decode BGZF blocks; the parser takes ~2 GB/s, which four
     // to six decoders fill
     reader.src.set_threads(std::max(1, std::min(6, threads / 4)));
+    reader.src.set_gzip_threads(threads / 2);
     if (!reader.src.open(cfg.reads_path, reader.error)) {
         fprintf(stderr, "tb_classify_fastx: %s\n", reader.error.c_str());
         tb_internal_set_error(reader.error.c_str());
@@ -1751,6 +2030,46 @@ int64_t tb_fastx_dump(const char *reads_path, int out_fd)
     return n;
 }
 
+
+// exposed for tests: the lines of a (possibly compressed) file as the parser sees them, written to
+// out_fd one after the other (line ends already translated to '\n').  Returns the number of bytes.
+int64_t tb_fastx_cat(const char *reads_path, int out_fd, int decode_threads)
+{
+    LineSource src;
+    std::string err;
+    src.set_threads(decode_threads);
+    src.set_gzip_threads(decode_threads);
+    if (!src.open(reads_path, err)) {
+        tb_internal_set_error(err.c_str());
+        return -1;
+    }
+    std::string out;
+    int64_t total = 0;
+    const char *lp;
+    size_t ln;
+    auto flush = [&]() {
+        size_t off = 0;
+        while (off < out.size()) {
+            const ssize_t w = ::write(out_fd, out.data() + off, out.size() - off);
+            if (w < 0 && errno == EINTR) continue;
+            if (w <= 0) return false;
+            off += (size_t)w;
+        }
+        out.clear();
+        return true;
+    };
+    while (src.next(lp, ln)) {
+        out.append(lp, ln);
+        total += (int64_t)ln;
+        if (out.size() >= (1u << 20) && !flush()) return -3;
+    }
+    if (!flush()) return -3;
+    if (!src.error().empty()) {
+        tb_internal_set_error(src.error().c_str());
+        return -2;
+    }
+    return total;
+}
 
 // exposed for tests: copy in_fd to the gzip file out_path through the pipeline's writer (chunks
 // compressed in parallel as independent members, written in order), feeding it `piece` bytes at a

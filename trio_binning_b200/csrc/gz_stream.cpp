@@ -951,6 +951,441 @@ long GzStream::read(char *dst, size_t cap)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// SpanInflate: DEFLATE from the middle of a stream, 16-bit symbols with window markers
+// (gz_stream.h has the scheme).  Slower per byte than GzStream (wider output, one careful
+// accounting of the bits per symbol) -- it exists to run on several cores at once.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct BitIn {
+    const unsigned char *base = nullptr, *p = nullptr, *end = nullptr;
+    uint64_t bb = 0;
+    unsigned bc = 0;
+    inline void refill()
+    {
+        if (end - p >= 8) {
+            bb |= load64(p) << bc;  // bits above bc are look-ahead of the same stream: OR-ing them again is harmless
+            p += (63 - bc) >> 3;
+            bc |= 56;
+        } else {
+            while (bc <= 56 && p < end) {
+                bb |= (uint64_t)*p++ << bc;
+                bc += 8;
+            }
+        }
+    }
+    void seek(uint64_t bit)
+    {
+        p = base + (bit >> 3);
+        bb = 0;
+        bc = 0;
+        refill();
+        const unsigned d = (unsigned)(bit & 7);
+        if (bc >= d) {
+            bb >>= d;
+            bc -= d;
+        } else {
+            bc = 0;
+        }
+    }
+    uint64_t bit_pos() const { return (uint64_t)(p - base) * 8 - bc; }
+    // drop the look-ahead and go back to whole bytes (stored blocks, trailers); returns the byte pointer
+    const unsigned char *align_to_byte()
+    {
+        const uint64_t bit = (bit_pos() + 7) & ~7ull;
+        p = base + (bit >> 3);
+        bb = 0;
+        bc = 0;
+        return p;
+    }
+};
+
+// Kraft sum of a set of code lengths: 0 complete, > 0 incomplete, < 0 over-subscribed
+int64_t kraft_left(const uint8_t *lens, unsigned n, unsigned *n_used)
+{
+    unsigned count[16] = { 0 };
+    unsigned used = 0;
+    for (unsigned s = 0; s < n; s++) {
+        count[lens[s]]++;
+        used += lens[s] != 0;
+    }
+    if (n_used) *n_used = used;
+    int64_t left = 1;
+    for (unsigned l = 1; l <= 15; l++) {
+        left = left * 2 - (int64_t)count[l];
+        if (left < 0) return -1;
+    }
+    return left;
+}
+
+}  // namespace
+
+struct SpanInflate::Tables {
+    uint32_t lit[(1u << LB) + 4608];
+    uint32_t dist[(1u << DB) + 4096];
+};
+
+SpanInflate::SpanInflate() : t_(new Tables())
+{
+    payloads();
+}
+SpanInflate::~SpanInflate() { delete t_; }
+
+size_t SpanInflate::member_header_length(const unsigned char *p, size_t n)
+{
+    if (n < 10 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || (p[3] & 0xE0)) return 0;
+    const unsigned flg = p[3];
+    size_t q = 10;
+    if (flg & 4) {
+        if (n < q + 2) return 0;
+        const size_t xlen = p[q] | ((size_t)p[q + 1] << 8);
+        q += 2;
+        if (n < q + xlen) return 0;
+        q += xlen;
+    }
+    for (unsigned bit = 8; bit <= 16; bit <<= 1) {
+        if (!(flg & bit)) continue;
+        const void *z = memchr(p + q, 0, n - q);
+        if (!z) return 0;
+        q = (size_t)((const unsigned char *)z - p) + 1;
+    }
+    if (flg & 2) {
+        if (n < q + 2) return 0;
+        q += 2;
+    }
+    return q;
+}
+
+bool resolve_markers(const uint16_t *sym, size_t n, const unsigned char *window, unsigned char *out)
+{
+    size_t i = 0;
+    unsigned bad = 0;
+#if defined(__x86_64__) && defined(__SSE2__)
+    for (; i + 16 <= n; i += 16) {
+        const __m128i a = _mm_loadu_si128((const __m128i *)(sym + i)), b = _mm_loadu_si128((const __m128i *)(sym + i + 8));
+        const __m128i hi = _mm_or_si128(_mm_srli_epi16(a, 8), _mm_srli_epi16(b, 8));
+        if (_mm_movemask_epi8(_mm_cmpeq_epi8(hi, _mm_setzero_si128())) == 0xFFFF) {
+            _mm_storeu_si128((__m128i *)(out + i), _mm_packus_epi16(a, b));  // sixteen plain bytes
+            continue;
+        }
+        for (size_t j = i; j < i + 16; j++) {
+            const unsigned s = sym[j];
+            if (s < 256) out[j] = (unsigned char)s;
+            else if (s < 256 + SpanResult::kWindow) out[j] = window[s - 256];
+            else bad = 1;
+        }
+    }
+#endif
+    for (; i < n; i++) {
+        const unsigned s = sym[i];
+        if (s < 256) out[i] = (unsigned char)s;
+        else if (s < 256 + SpanResult::kWindow) out[i] = window[s - 256];
+        else bad = 1;
+    }
+    return bad == 0;
+}
+
+namespace {
+
+// Dynamic block header (after the three header bits) into the tables.  strict: only what a real
+// encoder writes is accepted (complete codes) -- the filter of the start search.
+// 1 ok, -1 invalid, -2 input ends inside it
+int read_dynamic_header(BitIn &in, bool strict, uint32_t *lit_table, size_t lit_cap, uint32_t *dist_table, size_t dist_cap,
+                        const char *&problem)
+{
+#define S_TAKE(var, nb)                                   \
+    do {                                                  \
+        if (in.bc < (unsigned)(nb)) in.refill();          \
+        if (in.bc < (unsigned)(nb)) return -2;            \
+        var = (unsigned)(in.bb & ((1ull << (nb)) - 1));   \
+        in.bb >>= (nb);                                   \
+        in.bc -= (nb);                                    \
+    } while (0)
+    unsigned hlit, hdist, hclen;
+    S_TAKE(hlit, 5);
+    S_TAKE(hdist, 5);
+    S_TAKE(hclen, 4);
+    hlit += 257;
+    hdist += 1;
+    hclen += 4;
+    if (hlit > 286 || hdist > 30) { problem = "too many length or distance symbols"; return -1; }
+    uint8_t cl[19];
+    memset(cl, 0, 19);
+    for (unsigned i = 0; i < hclen; i++) {
+        unsigned v;
+        S_TAKE(v, 3);
+        cl[CLEN_ORDER[i]] = (uint8_t)v;
+    }
+    if (strict && kraft_left(cl, 19, nullptr) != 0) return -1;
+    uint32_t cl_payload[19], cl_table[1u << 7];
+    for (unsigned s = 0; s < 19; s++) cl_payload[s] = s << 16;
+    if (!build_table(cl, 19, cl_payload, 7, cl_table, 1u << 7)) { problem = "invalid code-length code"; return -1; }
+    uint8_t lens[320];
+    unsigned n = 0;
+    while (n < hlit + hdist) {
+        if (in.bc < 14) in.refill();
+        const uint32_t e = cl_table[in.bb & 127];
+        if (e & F_EXC) { problem = "invalid code-length symbol"; return -1; }
+        if ((e & 0xFF) > in.bc) return -2;
+        in.bb >>= (e & 63);
+        in.bc -= (e & 0xFF);
+        const unsigned sym = e >> 16;
+        if (sym < 16) {
+            lens[n++] = (uint8_t)sym;
+            continue;
+        }
+        unsigned rep, val = 0;
+        if (sym == 16) {
+            if (n == 0) { problem = "repeat without a previous length"; return -1; }
+            val = lens[n - 1];
+            S_TAKE(rep, 2);
+            rep += 3;
+        } else if (sym == 17) {
+            S_TAKE(rep, 3);
+            rep += 3;
+        } else {
+            S_TAKE(rep, 7);
+            rep += 11;
+        }
+        if (n + rep > hlit + hdist) { problem = "code lengths overrun"; return -1; }
+        while (rep--) lens[n++] = (uint8_t)val;
+    }
+#undef S_TAKE
+    if (lens[256] == 0) { problem = "no end-of-block code"; return -1; }
+    uint8_t ll[288], dl[32];
+    memset(ll, 0, sizeof ll);
+    memset(dl, 0, sizeof dl);
+    memcpy(ll, lens, hlit);
+    memcpy(dl, lens + hlit, hdist);
+    if (strict) {
+        if (kraft_left(ll, 288, nullptr) != 0) return -1;
+        unsigned used = 0;
+        const int64_t left = kraft_left(dl, 32, &used);
+        // zlib writes a complete distance code, or a single code of one bit when at most one distance is used
+        if (left < 0 || (left != 0 && !(used <= 1))) return -1;
+    }
+    if (!build_table(ll, 288, payloads().lit, LB, lit_table, lit_cap, true)) { problem = "invalid literal/length code"; return -1; }
+    if (!build_table(dl, 32, payloads().dist, DB, dist_table, dist_cap)) { problem = "invalid distance code"; return -1; }
+    return 1;
+}
+
+// Symbols of one Huffman block appended to sym[0..n).  min_pos: lowest index a match may reach.
+// 1 end of block, -1 error (problem set), -2 more than `limit` symbols without an end of block
+int decode_block_symbols(BitIn &in, const uint32_t *lt, const uint32_t *dt, std::vector<uint16_t> &sym, size_t &n_io,
+                         size_t min_pos, size_t limit, const char *&problem)
+{
+    size_t n = n_io;
+    uint16_t *o = sym.data();
+    size_t cap = sym.size();
+    int rc = 0;
+#define S_LOOKUP(e, table, PB, PM)                                                              \
+    do {                                                                                        \
+        e = table[in.bb & PM];                                                                  \
+        if (e & F_LINK) e = table[(e >> 16) + ((in.bb >> PB) & ((1u << ((e >> 8) & 15)) - 1))];  \
+    } while (0)
+#define S_CONSUME(nb)                                                               \
+    {                                                                               \
+        const unsigned nb_ = (nb);                                                  \
+        if (nb_ > in.bc) { problem = "truncated deflate stream"; rc = -1; break; }  \
+        in.bb >>= nb_;                                                              \
+        in.bc -= nb_;                                                               \
+    }
+#define S_LITERALS(e)                              \
+    S_CONSUME(e & 0xFF);                           \
+    o[n] = (uint16_t)((e >> 16) & 0xFF);           \
+    o[n + 1] = (uint16_t)(e >> 24);                \
+    n += 1 + ((e >> 14) & 1);
+    for (;;) {
+        if (n + 600 > cap) {
+            if (n > limit) { rc = -2; break; }
+            sym.resize(cap + cap / 2 + 65536);
+            o = sym.data();
+            cap = sym.size();
+        }
+        in.refill();
+        uint32_t e;
+        S_LOOKUP(e, lt, LB, LM);
+        if (e & F_LIT) {
+            // up to three table entries (six literals) per refill: 3 x 15 bits <= 56
+            S_LITERALS(e);
+            S_LOOKUP(e, lt, LB, LM);
+            if (e & F_LIT) {
+                S_LITERALS(e);
+                S_LOOKUP(e, lt, LB, LM);
+                if (e & F_LIT) {
+                    S_LITERALS(e);
+                    continue;
+                }
+            }
+            in.refill();
+        }
+        S_CONSUME(e & 0xFF);
+        if (e & F_EXC) {
+            if ((e & F_BAD) == F_BAD) { problem = "invalid literal/length code in the stream"; rc = -1; }
+            else rc = 1;
+            break;
+        }
+        // a match: <= 15 + 5 bits of length were in reach, <= 15 + 13 of distance follow (48 <= 56)
+        unsigned x = (e >> 8) & 15;
+        const unsigned length = (e >> 16) + (unsigned)(in.bb & ((1u << x) - 1));
+        S_CONSUME(x);
+        uint32_t d;
+        S_LOOKUP(d, dt, DB, DM);
+        if (d & F_EXC) { problem = "invalid distance code in the stream"; rc = -1; break; }
+        S_CONSUME(d & 0xFF);
+        x = (d >> 8) & 15;
+        const size_t dist = (d >> 16) + (size_t)(in.bb & ((1u << x) - 1));
+        S_CONSUME(x);
+        if (dist > n - min_pos) { problem = "match distance reaches before the start of the member"; rc = -1; break; }
+        const uint16_t *src = o + n - dist;
+        uint16_t *dst = o + n;
+        if (dist >= length) memcpy(dst, src, (size_t)length * 2);
+        else for (unsigned i = 0; i < length; i++) dst[i] = src[i];
+        n += length;
+    }
+#undef S_LOOKUP
+#undef S_CONSUME
+#undef S_LITERALS
+    n_io = n;
+    return rc;
+}
+
+void fixed_code_lengths(uint8_t *ll, uint8_t *dl)
+{
+    for (unsigned s = 0; s < 144; s++) ll[s] = 8;
+    for (unsigned s = 144; s < 256; s++) ll[s] = 9;
+    for (unsigned s = 256; s < 280; s++) ll[s] = 7;
+    for (unsigned s = 280; s < 288; s++) ll[s] = 8;
+    memset(dl, 5, 32);
+}
+
+}  // namespace
+
+void SpanInflate::decode(const unsigned char *file, uint64_t size, uint64_t start_bit, bool search, uint64_t end_bit,
+                         bool fresh_member, SpanResult &r)
+{
+    constexpr size_t W = SpanResult::kWindow;
+    r.start_bit = r.stop_bit = start_bit;
+    r.stop_fresh = false;
+    r.ends.clear();
+    r.tail = false;
+    r.tail_off = 0;
+    r.found = false;
+    r.error.clear();
+    if (r.sym.size() < W + (1u << 20)) r.sym.resize(W + (1u << 20));
+    for (size_t j = 0; j < W; j++) r.sym[j] = (uint16_t)(256 + j);
+    r.n_sym = W;
+    const uint64_t total_bits = size * 8;
+    BitIn in;
+    in.base = file;
+    in.end = file + size;
+    const char *problem = nullptr;
+    size_t min_pos = fresh_member ? W : 0;
+
+    if (search) {
+        // the first bit position where a dynamic block header passes the strict checks, the block
+        // decodes to its end and something that can be a block header follows
+        const size_t trial_limit = W + (8u << 20);
+        uint64_t b = start_bit;
+        for (; b < end_bit && b + 64 < total_bits; b++) {
+            const uint64_t peek = load64(file + (b >> 3)) >> (b & 7);  // >= 56 bits
+            if (((peek >> 1) & 3) != 2) continue;                       // BTYPE
+            if (((peek >> 3) & 31) > 29 || ((peek >> 8) & 31) > 29) continue;  // HLIT, HDIST
+            in.seek(b + 3);
+            if (read_dynamic_header(in, true, t_->lit, sizeof(t_->lit) / 4, t_->dist, sizeof(t_->dist) / 4, problem) != 1) continue;
+            size_t n = W;
+            if (decode_block_symbols(in, t_->lit, t_->dist, r.sym, n, 0, trial_limit, problem) != 1) continue;
+            if (n == W) continue;  // an empty block proves nothing
+            if (!(peek & 1)) {
+                // not the final block: the next three bits must be able to start a block
+                if (in.bc < 17) in.refill();
+                if (in.bc < 3) continue;
+                const unsigned type = (unsigned)(in.bb >> 1) & 3;
+                if (type == 3) continue;
+                if (type == 2 && in.bc >= 13 && ((((in.bb >> 3) & 31) > 29) || (((in.bb >> 8) & 31) > 29))) continue;
+            }
+            break;
+        }
+        if (b >= end_bit || b + 64 >= total_bits) return;  // found stays false
+        r.found = true;
+        r.start_bit = b;
+        problem = nullptr;
+    }
+
+    // ---- decode block after block from r.start_bit
+    in.seek(r.start_bit);
+    bool at_member_start = fresh_member;
+    for (;;) {
+        const uint64_t here = in.bit_pos();
+        if (here >= end_bit && here > r.start_bit) {
+            r.stop_bit = here;
+            r.stop_fresh = at_member_start;
+            return;
+        }
+        at_member_start = false;
+        if (in.bc < 3) in.refill();
+        if (in.bc < 3) { r.error = "truncated deflate stream"; return; }
+        const unsigned final_bit = (unsigned)in.bb & 1, type = (unsigned)(in.bb >> 1) & 3;
+        in.bb >>= 3;
+        in.bc -= 3;
+        if (type == 0) {
+            const unsigned char *q = in.align_to_byte();
+            if (in.end - q < 4) { r.error = "truncated stored block"; return; }
+            const unsigned len = q[0] | (q[1] << 8), nlen = q[2] | (q[3] << 8);
+            if ((len ^ nlen) != 0xFFFF) { r.error = "stored block length check failed"; return; }
+            q += 4;
+            if ((size_t)(in.end - q) < len) { r.error = "truncated stored block"; return; }
+            if (r.n_sym + len + 600 > r.sym.size()) r.sym.resize(r.n_sym + len + (1u << 20));
+            for (unsigned i = 0; i < len; i++) r.sym[r.n_sym + i] = q[i];
+            r.n_sym += len;
+            in.p = q + len;
+        } else if (type == 3) {
+            r.error = "invalid block type";
+            return;
+        } else {
+            if (type == 1) {
+                uint8_t ll[288], dl[32];
+                fixed_code_lengths(ll, dl);
+                build_table(ll, 288, payloads().lit, LB, t_->lit, sizeof(t_->lit) / 4, true);
+                build_table(dl, 32, payloads().dist, DB, t_->dist, sizeof(t_->dist) / 4);
+            } else {
+                const int h = read_dynamic_header(in, false, t_->lit, sizeof(t_->lit) / 4, t_->dist, sizeof(t_->dist) / 4, problem);
+                if (h != 1) {
+                    r.error = h == -2 ? "truncated deflate stream" : (problem ? problem : "invalid block header");
+                    return;
+                }
+            }
+            const int rc = decode_block_symbols(in, t_->lit, t_->dist, r.sym, r.n_sym, min_pos, (size_t)-1 >> 2, problem);
+            if (rc != 1) {
+                r.error = problem ? problem : "corrupt deflate stream";
+                return;
+            }
+        }
+        if (!final_bit) continue;
+        // ---- end of a member: trailer, then either another member or the serial reader's business
+        const unsigned char *q = in.align_to_byte();
+        if (in.end - q < 8) { r.error = "truncated gzip trailer"; return; }
+        SpanResult::MemberEnd me;
+        me.pos = r.n_sym;
+        me.crc = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
+        me.isize = q[4] | (q[5] << 8) | (q[6] << 16) | ((uint32_t)q[7] << 24);
+        q += 8;
+        me.next_off = (uint64_t)(q - file);
+        r.ends.push_back(me);
+        const size_t hdr = member_header_length(q, (size_t)(in.end - q));
+        if (hdr == 0) {
+            r.tail = true;
+            r.tail_off = (uint64_t)(q - file);
+            r.stop_bit = r.tail_off * 8;
+            return;
+        }
+        in.p = q + hdr;
+        min_pos = r.n_sym;  // the new member has no history
+        at_member_start = true;
+    }
+}
+
 }  // namespace tb
 
 // testing aid (include/trio_kmers_b200.h): decode `path` with GzStream and write the bytes to out_fd

@@ -82,6 +82,61 @@ private:
     std::string err_;
 };
 
+// ---------------------------------------------------------------------------------------------
+// Parallel decoding of ONE gzip stream ("parallel decode of plain gzip input").
+// A DEFLATE stream has no index, but it can be cut anyway: a worker that starts in the middle
+// (a) looks for the next bit position where a dynamic-Huffman block header parses, its codes are
+// complete and the block decodes to its end-of-block code, and (b) decodes from there without
+// knowing the 32 KiB of text before it: output symbols are 16 bits wide, 0..255 a byte, 256 + j
+// "whatever byte stands at position j of the unknown window"; matches copy such markers like any
+// other symbol.  Once the spans before it are resolved, the window is known and one pass turns the
+// markers into bytes.  Nothing is trusted: a span must begin exactly at the block boundary where
+// its predecessor stopped (else it is decoded again from there), and every member's CRC-32 and
+// ISIZE are checked as in the serial reader.  (The scheme is the published one of pugz /
+// rapidgzip; the code is this project's.)
+// ---------------------------------------------------------------------------------------------
+struct SpanResult {
+    static constexpr size_t kWindow = 32768;
+    uint64_t start_bit = 0;      // absolute bit offset in the file of the first block decoded
+    uint64_t stop_bit = 0;       // block boundary (first block of the next span) where decoding stopped
+    bool stop_fresh = false;     // ... and that block is the first of a member
+    std::vector<uint16_t> sym;   // kWindow markers, then the decoded symbols
+    size_t n_sym = 0;            // end of the decoded symbols in sym (>= kWindow)
+    struct MemberEnd {
+        size_t pos;              // index in sym where the member's data ends
+        uint32_t crc, isize;     // its trailer
+        uint64_t next_off;       // byte offset of what follows the trailer
+    };
+    std::vector<MemberEnd> ends;
+    bool tail = false;           // stopped after a member that is not followed by another member:
+    uint64_t tail_off = 0;       //   the serial reader continues at this byte offset (padding, garbage, EOF)
+    bool found = false;          // search mode: a start was found inside the search range
+    std::string error;           // a decode error after the start (invalid code, truncation, ...)
+};
+
+class SpanInflate {
+public:
+    SpanInflate();
+    ~SpanInflate();
+    // Decode blocks of file[0..size) into r, from the block header at `start_bit` (search = false)
+    // or from the first verifiable dynamic block header at or after it (search = true; given up at
+    // `end_bit`), until the first block boundary at or after `end_bit` or the end of the last member.
+    // fresh_member: start_bit is the first block of a member (no history may be referenced).
+    void decode(const unsigned char *file, uint64_t size, uint64_t start_bit, bool search, uint64_t end_bit,
+                bool fresh_member, SpanResult &r);
+    // Length of the gzip member header at p (RFC 1952), 0 if there is none / it is cut short.
+    static size_t member_header_length(const unsigned char *p, size_t n);
+
+private:
+    struct Tables;
+    Tables *t_;
+};
+
+// Markers -> bytes: out[i] = sym[i] < 256 ? sym[i] : window[sym[i] - 256] for the n symbols at sym;
+// window = the kWindow bytes before the span (window[kWindow - 1] the last one).  Returns false if
+// a symbol is out of range.
+bool resolve_markers(const uint16_t *sym, size_t n, const unsigned char *window, unsigned char *out);
+
 // CRC-32 as in gzip (zlib's crc32 semantics), PCLMULQDQ-accelerated where available
 uint32_t crc32_any(uint32_t crc, const unsigned char *p, size_t n);
 bool crc32_is_accelerated();

@@ -206,6 +206,8 @@ lib.tb_route_fastx.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_int, C.c_i
                                C.POINTER(StreamStats)]
 lib.tb_counter_create.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int]
 lib.tb_counter_create.restype = C.c_void_p
+lib.tb_fastx_cat.argtypes = [C.c_char_p, C.c_int, C.c_int]
+lib.tb_fastx_cat.restype = C.c_int64
 lib.tb_counter_slot_bytes.argtypes = [C.c_int]
 lib.tb_counter_slot_bytes.restype = C.c_int
 lib.tb_counter_destroy.argtypes = [C.c_void_p]
@@ -858,6 +860,21 @@ def fastx_dump(reads_path: str):
         out.append(tuple(fields))
     assert len(out) == n
     return out
+
+
+def fastx_cat(reads_path: str, decode_threads: int = 4) -> bytes:
+    """The text of a FASTA/FASTQ(.gz) file as the native reader's input stage delivers it to the
+    parser (testing aid, no GPU needed)."""
+    import tempfile
+
+    with tempfile.TemporaryFile() as tmp:
+        n = lib.tb_fastx_cat(os.fsencode(reads_path), tmp.fileno(), decode_threads)
+        if n < 0:
+            raise RuntimeError(f"tb_fastx_cat failed ({n}): {_error()}")
+        tmp.seek(0)
+        data = tmp.read()
+    assert len(data) == n
+    return data
 
 
 def gunzip(path: str, chunk: int = 0) -> bytes:
