@@ -435,6 +435,17 @@ private:
         bool search = false;
         bool done = false, taken = false;
         tb::SpanResult res;
+        // the symbols as bytes, the positions still to be patched from the window, and the chunk flags
+        std::vector<char> bytes;
+        std::vector<uint32_t> marker_pos;
+        bool has_cr = true, ascii = false, narrowed = false;
+        void narrow()
+        {
+            const size_t n = res.n_sym - tb::SpanResult::kWindow;
+            bytes.resize(n ? n : 1);
+            tb::narrow_symbols(res.sym.data() + tb::SpanResult::kWindow, n, (unsigned char *)bytes.data(), marker_pos, has_cr, ascii);
+            narrowed = true;
+        }
     };
     bool parallel_gzip() const { return gz_ && !bgzf_ && pgzip_ok_; }
 
@@ -453,7 +464,9 @@ private:
             }
             const auto t0 = Clock::now();
             try {
+                job->narrowed = false;
                 inflate.decode(map_, map_size_, job->start_bit, job->search, job->end_bit, !job->search, job->res);
+                if (job->res.error.empty() && (job->res.found || !job->search)) job->narrow();
             } catch (const std::exception &) {
                 job->res.found = false;
                 job->res.error = "out of memory while decoding";
@@ -533,15 +546,17 @@ private:
         int bad_streak = 0;
         bool speculate = true;
         uint64_t n_accepted = 0, n_redone = 0, n_covered = 0;
+        double resolve_s = 0, wait_s = 0;
         const bool debug = getenv("TB_PGZIP_DEBUG") != nullptr;
         auto report = [&](const char *how) {
             if (debug)
                 fprintf(stderr, "pgzip: %llu spans of %llu bytes on %d threads: %llu as guessed, %llu decoded again, %llu covered "
-                        "by a predecessor; %s\n", (unsigned long long)n_spans, (unsigned long long)S, gzip_threads_,
-                        (unsigned long long)n_accepted, (unsigned long long)n_redone, (unsigned long long)n_covered, how);
+                        "by a predecessor; this thread: %.2f s resolving, %.2f s waiting for spans; %s\n", (unsigned long long)n_spans,
+                        (unsigned long long)S, gzip_threads_, (unsigned long long)n_accepted, (unsigned long long)n_redone,
+                        (unsigned long long)n_covered, resolve_s, wait_s, how);
         };
         tb::SpanInflate own;               // for spans that have to be decoded again, in order
-        tb::SpanResult own_res;
+        SpanJob own_job;
 
         for (uint64_t k = 0; k < n_spans; k++) {
             while (speculate && issued < n_spans && issued < k + ahead) issue(issued++);
@@ -558,16 +573,18 @@ private:
                 n_covered++;
                 continue;
             }
-            tb::SpanResult *res = nullptr;
+            SpanJob *job = nullptr;
             if (speculate) {
                 SpanJob *j = ring[k % ahead].get();
                 {
+                    const auto tw = Clock::now();
                     std::unique_lock<std::mutex> lk(m_);
                     cv_.wait(lk, [&] { return stop_ || j->done; });
                     if (stop_) return;
+                    wait_s += seconds_since(tw);
                 }
                 if (k == 0 || (j->res.found && j->res.start_bit == expected)) {
-                    res = &j->res;
+                    job = j;
                     bad_streak = 0;
                     n_accepted++;
                 } else if (++bad_streak >= 3) {
@@ -577,34 +594,40 @@ private:
                     close_spans();
                 }
             }
-            if (!res) {
+            if (!job) {
                 const auto t0 = Clock::now();
+                own_job.narrowed = false;
                 try {
-                    own.decode(file, size, expected, false, end_bit, expected_fresh, own_res);
+                    own.decode(file, size, expected, false, end_bit, expected_fresh, own_job.res);
+                    if (own_job.res.error.empty()) own_job.narrow();
                 } catch (const std::exception &) {
-                    own_res.error = "out of memory while decoding";
+                    own_job.res.error = "out of memory while decoding";
                 }
                 inflate_ns_.fetch_add((uint64_t)(seconds_since(t0) * 1e9));
-                res = &own_res;
+                job = &own_job;
                 n_redone++;
             }
+            tb::SpanResult *res = &job->res;
+            if (res->error.empty() && !job->narrowed) res->error = "out of memory while decoding";
             if (!res->error.empty()) {
                 report(("serial reader takes the member again: " + res->error).c_str());
                 pgzip_fallback(member_start, member_delivered);
                 return;
             }
-            // ---- markers -> bytes, member by member; CRC-32 and ISIZE as the serial reader checks them
+            // ---- the markers the worker left open get their bytes from the window; then, member by
+            // ---- member, CRC-32 and ISIZE as the serial reader checks them
             const auto t0 = Clock::now();
             const size_t n = res->n_sym - W;
-            ChunkPtr c = fresh_chunk();
-            bool ok = true;
-            try {
-                c->data.resize(n ? n : 1);
-            } catch (const std::exception &) {
-                ok = false;
+            bool ok = true, has_cr = job->has_cr, ascii = job->ascii;
+            unsigned char *out = (unsigned char *)job->bytes.data();
+            for (const uint32_t pos : job->marker_pos) {
+                const unsigned m = res->sym[W + pos] - 256u;
+                if (m >= W) { ok = false; break; }
+                const unsigned char b = window[m];
+                out[pos] = b;
+                has_cr = has_cr || b == '\r';
+                ascii = ascii && b < 0x80;
             }
-            unsigned char *out = (unsigned char *)c->data.data();
-            ok = ok && tb::resolve_markers(res->sym.data() + W, n, window.data(), out);
             size_t from = 0;
             uint64_t next_member_start = member_start, delivered_after = member_delivered + n;
             for (size_t e = 0; ok && e < res->ends.size(); e++) {
@@ -619,7 +642,6 @@ private:
                 delivered_after = n - to;
             }
             if (!ok) {
-                free_chunk(c);
                 report("serial reader takes the member again: checksum, length or marker out of range");
                 pgzip_fallback(member_start, member_delivered);
                 return;
@@ -637,14 +659,17 @@ private:
             expected = res->stop_bit;
             expected_fresh = res->stop_fresh;
             bytes_in_ = expected / 8;
+            resolve_s += seconds_since(t0);
             inflate_ns_.fetch_add((uint64_t)(seconds_since(t0) * 1e9));
             if (n > 0) {
+                ChunkPtr c = fresh_chunk();
+                c->data.swap(job->bytes);  // the chunk's old buffer serves a later span
                 c->len = n;
-                c->scan_flags();
+                c->has_cr = has_cr;
+                c->ascii = ascii;
+                c->flags_known = true;
                 c->done = true;
                 if (!enqueue(c, false)) return;
-            } else {
-                free_chunk(c);
             }
             if (res->tail) {
                 // padding, garbage or the end of the file: the serial reader's rules apply
@@ -732,7 +757,7 @@ private:
     std::vector<std::unique_ptr<SpanJob>> span_ring_;
     bool spans_closed_ = false, pgzip_ok_ = false;
     const unsigned char *map_ = nullptr;
-    uint64_t map_size_ = 0, span_bytes_ = 2u << 20;
+    uint64_t map_size_ = 0, span_bytes_ = 1u << 20;
     std::vector<ChunkPtr> free_;
     size_t max_in_flight_ = 3;
     ChunkPtr cur_chunk_;
@@ -1932,6 +1957,7 @@ int tb_counter_add_fastx(tb_kmer_counter *counter, const char *reads_path, int64
     reader.batch_bases = std::max<int64_t>(1, batch_bases);
     int threads = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
     reader.src.set_threads(std::max(1, std::min(6, threads / 2)));
+    reader.src.set_gzip_threads(threads - 2);  // counting has no compressor competing for the cores
     if (!reader.src.open(reads_path, reader.error)) {
         tb_internal_set_error(reader.error.c_str());
         return -2;

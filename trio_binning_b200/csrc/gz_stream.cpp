@@ -1057,33 +1057,70 @@ size_t SpanInflate::member_header_length(const unsigned char *p, size_t n)
     return q;
 }
 
-bool resolve_markers(const uint16_t *sym, size_t n, const unsigned char *window, unsigned char *out)
+namespace {
+
+inline void narrow_slow(const uint16_t *sym, size_t from, size_t to, unsigned char *out, std::vector<uint32_t> &marker_pos,
+                        unsigned &any_or, unsigned &any_cr)
 {
+    for (size_t j = from; j < to; j++) {
+        const unsigned s = sym[j];
+        if (s < 256) {
+            out[j] = (unsigned char)s;
+            any_or |= s;
+            any_cr |= s == '\r';
+        } else {
+            out[j] = 0;
+            marker_pos.push_back((uint32_t)j);
+        }
+    }
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void narrow_avx2(const uint16_t *sym, size_t n, unsigned char *out,
+                                                 std::vector<uint32_t> &marker_pos, unsigned &any_or, unsigned &any_cr)
+{
+    __m256i acc_or = _mm256_setzero_si256(), acc_cr = _mm256_setzero_si256();
+    const __m256i cr = _mm256_set1_epi8('\r');
     size_t i = 0;
-    unsigned bad = 0;
-#if defined(__x86_64__) && defined(__SSE2__)
-    for (; i + 16 <= n; i += 16) {
-        const __m128i a = _mm_loadu_si128((const __m128i *)(sym + i)), b = _mm_loadu_si128((const __m128i *)(sym + i + 8));
-        const __m128i hi = _mm_or_si128(_mm_srli_epi16(a, 8), _mm_srli_epi16(b, 8));
-        if (_mm_movemask_epi8(_mm_cmpeq_epi8(hi, _mm_setzero_si128())) == 0xFFFF) {
-            _mm_storeu_si128((__m128i *)(out + i), _mm_packus_epi16(a, b));  // sixteen plain bytes
+    for (; i + 32 <= n; i += 32) {
+        const __m256i a = _mm256_loadu_si256((const __m256i *)(sym + i)), b = _mm256_loadu_si256((const __m256i *)(sym + i + 16));
+        if (!_mm256_testz_si256(_mm256_or_si256(a, b), _mm256_set1_epi16((short)0xFF00))) {
+            narrow_slow(sym, i, i + 32, out, marker_pos, any_or, any_cr);
             continue;
         }
-        for (size_t j = i; j < i + 16; j++) {
-            const unsigned s = sym[j];
-            if (s < 256) out[j] = (unsigned char)s;
-            else if (s < 256 + SpanResult::kWindow) out[j] = window[s - 256];
-            else bad = 1;
-        }
+        // thirty-two plain bytes: pack (per 128-bit lane), then put the lanes back in order
+        const __m256i v = _mm256_permute4x64_epi64(_mm256_packus_epi16(a, b), 0xD8);
+        _mm256_storeu_si256((__m256i *)(out + i), v);
+        acc_or = _mm256_or_si256(acc_or, v);
+        acc_cr = _mm256_or_si256(acc_cr, _mm256_cmpeq_epi8(v, cr));
     }
+    narrow_slow(sym, i, n, out, marker_pos, any_or, any_cr);
+    any_or |= _mm256_movemask_epi8(acc_or) ? 0x80u : 0u;  // only the high bits matter (ASCII or not)
+    any_cr |= _mm256_movemask_epi8(acc_cr) ? 1u : 0u;
+}
 #endif
-    for (; i < n; i++) {
-        const unsigned s = sym[i];
-        if (s < 256) out[i] = (unsigned char)s;
-        else if (s < 256 + SpanResult::kWindow) out[i] = window[s - 256];
-        else bad = 1;
+
+}  // namespace
+
+void narrow_symbols(const uint16_t *sym, size_t n, unsigned char *out, std::vector<uint32_t> &marker_pos, bool &has_cr,
+                    bool &ascii)
+{
+    unsigned any_or = 0, any_cr = 0;
+    marker_pos.clear();
+    if (n >> 32) {  // positions are 32 bits wide; no span comes near
+        for (size_t j = 0; j < n; j++) out[j] = 0;
+        has_cr = true;
+        ascii = false;
+        return;
     }
-    return bad == 0;
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) narrow_avx2(sym, n, out, marker_pos, any_or, any_cr);
+    else
+#endif
+        narrow_slow(sym, 0, n, out, marker_pos, any_or, any_cr);
+    has_cr = any_cr != 0;
+    ascii = (any_or & 0x80u) == 0;
 }
 
 namespace {

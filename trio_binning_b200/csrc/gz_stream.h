@@ -132,10 +132,13 @@ private:
     Tables *t_;
 };
 
-// Markers -> bytes: out[i] = sym[i] < 256 ? sym[i] : window[sym[i] - 256] for the n symbols at sym;
-// window = the kWindow bytes before the span (window[kWindow - 1] the last one).  Returns false if
-// a symbol is out of range.
-bool resolve_markers(const uint16_t *sym, size_t n, const unsigned char *window, unsigned char *out);
+// The decoded symbols as bytes, for the worker to do while the spans before it are still being
+// resolved: out[i] = sym[i] where that is a byte, 0 and an entry in marker_pos where it is a marker
+// (the one who knows the window patches those: out[p] = window[sym[p] - 256], window[kWindow - 1]
+// being the byte just before the span).  has_cr / ascii: whether the plain bytes hold a '\r', and
+// whether all of them are below 0x80 -- what the line reader wants to know about a chunk.
+void narrow_symbols(const uint16_t *sym, size_t n, unsigned char *out, std::vector<uint32_t> &marker_pos, bool &has_cr,
+                    bool &ascii);
 
 // CRC-32 as in gzip (zlib's crc32 semantics), PCLMULQDQ-accelerated where available
 uint32_t crc32_any(uint32_t crc, const unsigned char *p, size_t n);
