@@ -546,7 +546,7 @@ def run_pipeline_leg(kmers, synth, A, B, k, keys_a, keys_b, gbases):
     return {"what": "native pipeline, file -> three files + TSV, one GPU, inside one process (start-up and set build "
                     "excluded); seconds.parse is the reader thread's wall time, inflate / deflate_cpu are summed over "
                     "their threads, gpu_wait over the device workers",
-            "reads": n_reads, "bases": total, "fastq_bytes": size, "gzip_input": "4 MiB members, zlib -6 (decoded serially, like one member)", "host_threads": os.cpu_count(),
+            "reads": n_reads, "bases": total, "fastq_bytes": size, "gzip_input": "4 MiB members, zlib -6, no index (read as one gzip stream: cut into 1 MB spans and decoded on several cores, csrc/gz_stream.cpp SpanInflate)", "host_threads": os.cpu_count(),
             "generate_s": round(gen_s, 1), "runs": runs}
 
 

@@ -1288,6 +1288,9 @@ int decode_block_symbols(BitIn &in, const uint32_t *lt, const uint32_t *dt, std:
     return rc;
 }
 
+// symbols one span may decode to (128 MB of them): a megabyte of FASTQ is 4-5 MB of text
+constexpr size_t kMaxSpanSymbols = SpanResult::kWindow + (64u << 20);
+
 void fixed_code_lengths(uint8_t *ll, uint8_t *dl)
 {
     for (unsigned s = 0; s < 144; s++) ll[s] = 8;
@@ -1373,6 +1376,7 @@ void SpanInflate::decode(const unsigned char *file, uint64_t size, uint64_t star
             if ((len ^ nlen) != 0xFFFF) { r.error = "stored block length check failed"; return; }
             q += 4;
             if ((size_t)(in.end - q) < len) { r.error = "truncated stored block"; return; }
+            if (r.n_sym > kMaxSpanSymbols) { r.error = "span too large to hold"; return; }
             if (r.n_sym + len + 600 > r.sym.size()) r.sym.resize(r.n_sym + len + (1u << 20));
             for (unsigned i = 0; i < len; i++) r.sym[r.n_sym + i] = q[i];
             r.n_sym += len;
@@ -1393,9 +1397,10 @@ void SpanInflate::decode(const unsigned char *file, uint64_t size, uint64_t star
                     return;
                 }
             }
-            const int rc = decode_block_symbols(in, t_->lit, t_->dist, r.sym, r.n_sym, min_pos, (size_t)-1 >> 2, problem);
+            const int rc = decode_block_symbols(in, t_->lit, t_->dist, r.sym, r.n_sym, min_pos, kMaxSpanSymbols, problem);
             if (rc != 1) {
-                r.error = problem ? problem : "corrupt deflate stream";
+                // -2: text that expands this much is for the serial reader and its bounded memory
+                r.error = rc == -2 ? "span too large to hold" : (problem ? problem : "corrupt deflate stream");
                 return;
             }
         }
