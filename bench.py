@@ -494,6 +494,65 @@ def run_other_workload(name, kmers, synth, args, gather):
     return out
 
 
+def run_counter_leg(kmers):
+    """find-unique-kmers' compute beside the headline (N = 1 only): two read
+    libraries (150-base reads, 30 x of a 5-Mbase genome and of a haplotype 0.5 % away from it, 0.5 %
+    errors) counted at k = 21 from page-locked memory, both histograms, the reference's cut-off
+    search, both subtractions.  tools/count_bench.py is the full-size version with a CPU port beside
+    it.  Never fatal for the bench line: a failure is reported in place of the numbers."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import count_bench as cbench
+        from trio_binning_b200 import find_unique_kmers as fuk
+
+        k, genome_size, coverage, read_len, err = 21, 5_000_000, 30.0, 150, 0.005
+        rng = np.random.default_rng(11)
+        genome_a = cbench.ACGT[rng.integers(0, 4, genome_size)]
+        genome_b = genome_a.copy()
+        snp = rng.integers(0, genome_size, genome_size // 200)
+        genome_b[snp] = cbench.ACGT[(rng.integers(1, 4, len(snp)) + cbench.CODE[genome_b[snp]]) % 4]
+        libs = []
+        for genome in (genome_a, genome_b):
+            bases, offsets = cbench.library(genome, coverage, read_len, err, rng)
+            pin = kmers.PinnedBuffer(len(bases), np.uint8)
+            pin.array[:] = bases
+            libs.append((pin, offsets))
+        n_bases = sum(len(pin.array) for pin, _ in libs)
+        n_slots = int((genome_size + n_bases / 2 * err * k) * 1.6)
+
+        def one_pass():
+            t = {}
+            counters = [kmers.KmerCounter(k, n_slots) for _ in libs]
+            t0 = time.perf_counter()
+            for c, (pin, offsets) in zip(counters, libs):
+                c.add_packed(pin.array, offsets)
+            stats = [c.stats() for c in counters]
+            t["count"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            hists = [c.histogram(256) for c in counters]
+            t["histograms"] = time.perf_counter() - t0
+            cuts = [fuk.analyze_histogram(fuk.histogram_lines(h)) for h in hists]
+            t0 = time.perf_counter()
+            unique = [len(counters[0].select_unique(counters[1], *cuts[0])), len(counters[1].select_unique(counters[0], *cuts[1]))]
+            t["subtract_select_sort"] = time.perf_counter() - t0
+            for c in counters:
+                c.close()
+            return t, stats, cuts, unique
+
+        one_pass()
+        t, stats, cuts, unique = one_pass()
+        for pin, _ in libs:
+            pin.free()
+        return {"metric": "find_unique_kmers_read_bases_counted_per_second", "value": n_bases / t["count"], "unit": UNIT, "k": k,
+                "workload": f"2 libraries x {coverage:g}x of a {genome_size / 1e6:g}-Mbase genome, {read_len}-base reads",
+                "bases": n_bases, "windows_counted": sum(s["windows"] for s in stats),
+                "distinct": [s["distinct"] for s in stats], "slot_bytes": kmers.lib.tb_counter_slot_bytes(k),
+                "seconds": t, "cutoffs": [list(c) for c in cuts], "unique_kmers": unique,
+                "input": "ASCII in page-locked host memory, H2D inside the timed region"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
 def run_pipeline_leg(kmers, synth, A, B, k, keys_a, keys_b, gbases):
     """file -> files through the native pipeline on a bounded synthetic FASTQ (HiFi-like: 15 kb
     reads, run-length qualities), one GPU: plain, gzip and BGZF input; FASTQ-aware encoder and
@@ -787,6 +846,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                 if name != args.workload:
                     others[name] = run_other_workload(name, kmers, synth, args, gather)
             line["other_workloads"] = others
+            line["find_unique_kmers"] = run_counter_leg(kmers)
         print(json.dumps(line), flush=True)
     dist.close()
     return 0
