@@ -41,3 +41,20 @@ def test_two_rank_gloo_reduce_and_barrier():
         assert p.exitcode == 0
     # whole-job throughput = all ranks' bases over the slowest rank's time
     assert got[0] == got[1] == (11.0, 3000.0)
+
+
+def test_optional_bench_legs_never_break_the_line():
+    """bench.py's find-unique-kmers leg is an extra: whatever goes wrong inside it (here: no GPU)
+    must come back as an `error` field, not as an exception that would cost the whole JSON line."""
+    import sys
+
+    from conftest import ROOT
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from trio_binning_b200 import kmers
+
+    if kmers.device_count() > 0:
+        pytest.skip("a GPU is present")
+    out = bench.run_counter_leg(kmers)
+    assert set(out) == {"error"} and "no CPU fallback" in out["error"]
