@@ -178,3 +178,32 @@ def test_records_through_the_parser(kmers, spans, tmp_path):
     want = kmers.fastx_dump(path)
     spans(4096, enabled=True)
     assert kmers.fastx_dump(path) == want and len(want) == 200
+
+
+def test_random_streams_and_spans(kmers, spans, tmp_path):
+    """Randomised: text kinds x zlib levels / strategies / window sizes x member layouts x span sizes."""
+    rng = np.random.default_rng(2026)
+    kinds = {
+        "long": lambda: _fastq(int(rng.integers(5, 40)), int(rng.integers(2000, 12_000)), int(rng.integers(1 << 30))),
+        "short": lambda: _fastq(int(rng.integers(200, 1500)), 150, int(rng.integers(1 << 30)), qual_symbols=4),
+        "fasta": lambda: b"".join(b">c%d\n" % i + rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), 7000).tobytes() + b"\n"
+                                  for i in range(int(rng.integers(3, 30)))),
+        "repeats": lambda: (b"@r\n" + b"ACGT" * 500 + b"\n+\n" + b"I" * 2000 + b"\n") * int(rng.integers(20, 300)),
+    }
+    strategies = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]
+    for trial in range(25):
+        members, text = [], []
+        for _ in range(int(rng.integers(1, 4))):
+            t = kinds[str(rng.choice(list(kinds)))]()
+            co = zlib.compressobj(int(rng.integers(1, 10)), zlib.DEFLATED, 16 + int(rng.integers(9, 16)), int(rng.integers(1, 10)),
+                                  int(rng.choice(strategies)))
+            members.append(co.compress(t) + co.flush())
+            text.append(t)
+            if rng.random() < 0.3:
+                members.append(b"\0" * int(rng.integers(1, 3000)))
+        blob, want = b"".join(members), b"".join(text)
+        assert gzip.decompress(blob) == want
+        path = str(tmp_path / f"t{trial}.fq.gz")
+        open(path, "wb").write(blob)
+        spans(int(rng.integers(1024, 80_000)))
+        assert kmers.fastx_cat(path, int(rng.integers(1, 9))) == want, trial
