@@ -438,17 +438,6 @@ private:
         bool search = false;
         bool done = false, taken = false;
         tb::SpanResult res;
-        // the symbols as bytes, the positions still to be patched from the window, and the chunk flags
-        std::vector<char> bytes;
-        std::vector<uint32_t> marker_pos;
-        bool has_cr = true, ascii = false, narrowed = false;
-        void narrow()
-        {
-            const size_t n = res.n_sym - tb::SpanResult::kWindow;
-            bytes.resize(n ? n : 1);
-            tb::narrow_symbols(res.sym.data() + tb::SpanResult::kWindow, n, (unsigned char *)bytes.data(), marker_pos, has_cr, ascii);
-            narrowed = true;
-        }
     };
     bool parallel_gzip() const { return gz_ && !bgzf_ && pgzip_ok_; }
 
@@ -467,9 +456,7 @@ private:
             }
             const auto t0 = Clock::now();
             try {
-                job->narrowed = false;
                 inflate.decode(map_, map_size_, job->start_bit, job->search, job->end_bit, !job->search, job->res);
-                if (job->res.error.empty() && (job->res.found || !job->search)) job->narrow();
             } catch (const std::exception &) {
                 job->res.found = false;
                 job->res.error = "out of memory while decoding";
@@ -599,10 +586,8 @@ private:
             }
             if (!job) {
                 const auto t0 = Clock::now();
-                own_job.narrowed = false;
                 try {
                     own.decode(file, size, expected, false, end_bit, expected_fresh, own_job.res);
-                    if (own_job.res.error.empty()) own_job.narrow();
                 } catch (const std::exception &) {
                     own_job.res.error = "out of memory while decoding";
                 }
@@ -611,7 +596,6 @@ private:
                 n_redone++;
             }
             tb::SpanResult *res = &job->res;
-            if (res->error.empty() && !job->narrowed) res->error = "out of memory while decoding";
             if (!res->error.empty()) {
                 report(("serial reader takes the member again: " + res->error).c_str());
                 pgzip_fallback(member_start, member_delivered);
@@ -620,10 +604,10 @@ private:
             // ---- the markers the worker left open get their bytes from the window; then, member by
             // ---- member, CRC-32 and ISIZE as the serial reader checks them
             const auto t0 = Clock::now();
-            const size_t n = res->n_sym - W;
-            bool ok = true, has_cr = job->has_cr, ascii = job->ascii;
-            unsigned char *out = (unsigned char *)job->bytes.data();
-            for (const uint32_t pos : job->marker_pos) {
+            const size_t n = res->n_out;
+            bool ok = true, has_cr = res->has_cr, ascii = res->ascii;
+            unsigned char *out = (unsigned char *)res->bytes.data();
+            for (const uint32_t pos : res->marker_pos) {
                 const unsigned m = res->sym[W + pos] - 256u;
                 if (m >= W) { ok = false; break; }
                 const unsigned char b = window[m];
@@ -634,7 +618,7 @@ private:
             size_t from = 0;
             uint64_t next_member_start = member_start, delivered_after = member_delivered + n;
             for (size_t e = 0; ok && e < res->ends.size(); e++) {
-                const size_t to = res->ends[e].pos - W;
+                const size_t to = res->ends[e].pos;
                 crc = tb::crc32_any(crc, out + from, to - from);
                 member_len += to - from;
                 if (crc != res->ends[e].crc || (uint32_t)member_len != res->ends[e].isize) ok = false;
@@ -666,7 +650,7 @@ private:
             inflate_ns_.fetch_add((uint64_t)(seconds_since(t0) * 1e9));
             if (n > 0) {
                 ChunkPtr c = fresh_chunk();
-                c->data.swap(job->bytes);  // the chunk's old buffer serves a later span
+                c->data.swap(res->bytes);  // the chunk's old buffer serves a later span
                 c->len = n;
                 c->has_cr = has_cr;
                 c->ascii = ascii;

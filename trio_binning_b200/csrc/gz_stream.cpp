@@ -1209,11 +1209,12 @@ int read_dynamic_header(BitIn &in, bool strict, uint32_t *lit_table, size_t lit_
 
 // Symbols of one Huffman block appended to sym[0..n).  min_pos: lowest index a match may reach.
 // 1 end of block, -1 error (problem set), -2 more than `limit` symbols without an end of block
-int decode_block_symbols(BitIn &in, const uint32_t *lt, const uint32_t *dt, std::vector<uint16_t> &sym, size_t &n_io,
+template <class T>  // uint16_t: bytes and window markers; char: bytes only (no marker within reach any more)
+int decode_block_symbols(BitIn &in, const uint32_t *lt, const uint32_t *dt, std::vector<T> &sym, size_t &n_io,
                          size_t min_pos, size_t limit, const char *&problem)
 {
     size_t n = n_io;
-    uint16_t *o = sym.data();
+    T *o = sym.data();
     size_t cap = sym.size();
     int rc = 0;
 #define S_LOOKUP(e, table, PB, PM)                                                              \
@@ -1230,8 +1231,8 @@ int decode_block_symbols(BitIn &in, const uint32_t *lt, const uint32_t *dt, std:
     }
 #define S_LITERALS(e)                              \
     S_CONSUME(e & 0xFF);                           \
-    o[n] = (uint16_t)((e >> 16) & 0xFF);           \
-    o[n + 1] = (uint16_t)(e >> 24);                \
+    o[n] = (T)((e >> 16) & 0xFF);                  \
+    o[n + 1] = (T)(e >> 24);                       \
     n += 1 + ((e >> 14) & 1);
     for (;;) {
         if (n + 600 > cap) {
@@ -1275,9 +1276,10 @@ int decode_block_symbols(BitIn &in, const uint32_t *lt, const uint32_t *dt, std:
         const size_t dist = (d >> 16) + (size_t)(in.bb & ((1u << x) - 1));
         S_CONSUME(x);
         if (dist > n - min_pos) { problem = "match distance reaches before the start of the member"; rc = -1; break; }
-        const uint16_t *src = o + n - dist;
-        uint16_t *dst = o + n;
-        if (dist >= length) memcpy(dst, src, (size_t)length * 2);
+        const T *src = o + n - dist;
+        T *dst = o + n;
+        if (dist >= length) memcpy(dst, src, (size_t)length * sizeof(T));
+        else if (sizeof(T) == 1 && dist == 1) memset(dst, (int)(unsigned char)*src, length);
         else for (unsigned i = 0; i < length; i++) dst[i] = src[i];
         n += length;
     }
@@ -1290,6 +1292,23 @@ int decode_block_symbols(BitIn &in, const uint32_t *lt, const uint32_t *dt, std:
 
 // symbols one span may decode to (128 MB of them): a megabyte of FASTQ is 4-5 MB of text
 constexpr size_t kMaxSpanSymbols = SpanResult::kWindow + (64u << 20);
+
+// index just past the last marker among sym[from..to), or `before` if there is none (coarse: to the
+// end of the group of 32 symbols the marker sits in)
+size_t last_marker_end(const uint16_t *sym, size_t from, size_t to, size_t before)
+{
+    size_t last = before, i = from;
+#if defined(__x86_64__)
+    for (; i + 16 <= to; i += 16) {
+        const __m128i a = _mm_loadu_si128((const __m128i *)(sym + i)), b = _mm_loadu_si128((const __m128i *)(sym + i + 8));
+        const __m128i hi = _mm_or_si128(_mm_srli_epi16(a, 8), _mm_srli_epi16(b, 8));
+        if (_mm_movemask_epi8(_mm_cmpeq_epi8(hi, _mm_setzero_si128())) != 0xFFFF) last = i + 16;
+    }
+#endif
+    for (; i < to; i++)
+        if (sym[i] >= 256) last = i + 1;
+    return last;
+}
 
 void fixed_code_lengths(uint8_t *ll, uint8_t *dl)
 {
@@ -1353,14 +1372,50 @@ void SpanInflate::decode(const unsigned char *file, uint64_t size, uint64_t star
         problem = nullptr;
     }
 
-    // ---- decode block after block from r.start_bit
+    // ---- decode block after block from r.start_bit.  Symbols are 16 bits wide while a marker is
+    // ---- within reach of a match (the last 32 KiB); once it is not, the rest of the span is plain
+    // ---- bytes, decoded straight into the buffer the parser will read.
     in.seek(r.start_bit);
     bool at_member_start = fresh_member;
+    bool wide = !fresh_member;  // the first block of a member cannot reach back at all
+    size_t marker_end = W;      // sym index just past the last marker (the prefix is all markers)
+    size_t nb = 0;              // bytes in r.bytes once narrow
+    size_t min_pos_b = 0;
+    r.n_wide = 0;
+    r.marker_pos.clear();
+    r.has_cr = false;
+    r.ascii = true;
+    if (r.bytes.size() < (1u << 20)) r.bytes.resize(1u << 20);
+    auto go_narrow = [&]() {
+        const size_t n1 = r.n_sym - W;
+        if (r.bytes.size() < n1 + (1u << 20)) r.bytes.resize(n1 + n1 / 2 + (1u << 20));
+        narrow_symbols(r.sym.data() + W, n1, (unsigned char *)r.bytes.data(), r.marker_pos, r.has_cr, r.ascii);
+        r.n_wide = n1;
+        nb = n1;
+        min_pos_b = min_pos > W ? min_pos - W : 0;
+        wide = false;
+    };
+    auto finish = [&]() {
+        if (wide) go_narrow();
+        // what the line reader wants to know about the bytes that never were symbols
+        const unsigned char *q = (const unsigned char *)r.bytes.data() + r.n_wide;
+        const size_t m = nb - r.n_wide;
+        if (m) {
+            if (memchr(q, '\r', m)) r.has_cr = true;
+            uint64_t acc = 0;
+            size_t i = 0;
+            for (; i + 8 <= m; i += 8) acc |= load64(q + i);
+            for (; i < m; i++) acc |= q[i];
+            if (acc & 0x8080808080808080ull) r.ascii = false;
+        }
+        r.n_out = nb;
+    };
     for (;;) {
         const uint64_t here = in.bit_pos();
         if (here >= end_bit && here > r.start_bit) {
             r.stop_bit = here;
             r.stop_fresh = at_member_start;
+            finish();
             return;
         }
         at_member_start = false;
@@ -1369,6 +1424,7 @@ void SpanInflate::decode(const unsigned char *file, uint64_t size, uint64_t star
         const unsigned final_bit = (unsigned)in.bb & 1, type = (unsigned)(in.bb >> 1) & 3;
         in.bb >>= 3;
         in.bc -= 3;
+        const size_t block_from = r.n_sym;
         if (type == 0) {
             const unsigned char *q = in.align_to_byte();
             if (in.end - q < 4) { r.error = "truncated stored block"; return; }
@@ -1376,10 +1432,16 @@ void SpanInflate::decode(const unsigned char *file, uint64_t size, uint64_t star
             if ((len ^ nlen) != 0xFFFF) { r.error = "stored block length check failed"; return; }
             q += 4;
             if ((size_t)(in.end - q) < len) { r.error = "truncated stored block"; return; }
-            if (r.n_sym > kMaxSpanSymbols) { r.error = "span too large to hold"; return; }
-            if (r.n_sym + len + 600 > r.sym.size()) r.sym.resize(r.n_sym + len + (1u << 20));
-            for (unsigned i = 0; i < len; i++) r.sym[r.n_sym + i] = q[i];
-            r.n_sym += len;
+            if ((wide ? r.n_sym : nb) > kMaxSpanSymbols) { r.error = "span too large to hold"; return; }
+            if (wide) {
+                if (r.n_sym + len + 600 > r.sym.size()) r.sym.resize(r.n_sym + len + (1u << 20));
+                for (unsigned i = 0; i < len; i++) r.sym[r.n_sym + i] = q[i];
+                r.n_sym += len;
+            } else {
+                if (nb + len + 600 > r.bytes.size()) r.bytes.resize(nb + len + (1u << 20));
+                memcpy(r.bytes.data() + nb, q, len);
+                nb += len;
+            }
             in.p = q + len;
         } else if (type == 3) {
             r.error = "invalid block type";
@@ -1397,19 +1459,24 @@ void SpanInflate::decode(const unsigned char *file, uint64_t size, uint64_t star
                     return;
                 }
             }
-            const int rc = decode_block_symbols(in, t_->lit, t_->dist, r.sym, r.n_sym, min_pos, kMaxSpanSymbols, problem);
+            const int rc = wide ? decode_block_symbols(in, t_->lit, t_->dist, r.sym, r.n_sym, min_pos, kMaxSpanSymbols, problem)
+                                : decode_block_symbols(in, t_->lit, t_->dist, r.bytes, nb, min_pos_b, kMaxSpanSymbols, problem);
             if (rc != 1) {
                 // -2: text that expands this much is for the serial reader and its bounded memory
                 r.error = rc == -2 ? "span too large to hold" : (problem ? problem : "corrupt deflate stream");
                 return;
             }
         }
+        if (wide) {
+            marker_end = last_marker_end(r.sym.data(), block_from, r.n_sym, marker_end);
+            if (r.n_sym - marker_end >= W) go_narrow();
+        }
         if (!final_bit) continue;
         // ---- end of a member: trailer, then either another member or the serial reader's business
         const unsigned char *q = in.align_to_byte();
         if (in.end - q < 8) { r.error = "truncated gzip trailer"; return; }
         SpanResult::MemberEnd me;
-        me.pos = r.n_sym;
+        me.pos = wide ? r.n_sym - W : nb;
         me.crc = q[0] | (q[1] << 8) | (q[2] << 16) | ((uint32_t)q[3] << 24);
         me.isize = q[4] | (q[5] << 8) | (q[6] << 16) | ((uint32_t)q[7] << 24);
         q += 8;
@@ -1420,10 +1487,12 @@ void SpanInflate::decode(const unsigned char *file, uint64_t size, uint64_t star
             r.tail = true;
             r.tail_off = (uint64_t)(q - file);
             r.stop_bit = r.tail_off * 8;
+            finish();
             return;
         }
         in.p = q + hdr;
-        min_pos = r.n_sym;  // the new member has no history
+        if (wide) min_pos = r.n_sym;  // the new member has no history
+        else min_pos_b = nb;
         at_member_start = true;
     }
 }

@@ -100,10 +100,19 @@ struct SpanResult {
     uint64_t start_bit = 0;      // absolute bit offset in the file of the first block decoded
     uint64_t stop_bit = 0;       // block boundary (first block of the next span) where decoding stopped
     bool stop_fresh = false;     // ... and that block is the first of a member
-    std::vector<uint16_t> sym;   // kWindow markers, then the decoded symbols
-    size_t n_sym = 0;            // end of the decoded symbols in sym (>= kWindow)
+    // The text of the span.  Its first n_wide bytes were decoded as 16-bit symbols (sym[kWindow + i]):
+    // where marker_pos says so, bytes[i] is still open and sym[kWindow + i] - 256 is the position in
+    // the window before the span that holds it.  From the point where the last 32 KiB held no marker
+    // the decoder wrote bytes directly.
+    std::vector<char> bytes;
+    size_t n_out = 0;            // bytes of text
+    size_t n_wide = 0;
+    std::vector<uint32_t> marker_pos;
+    bool has_cr = false, ascii = true;  // a '\r' among the known bytes; all known bytes below 0x80
+    std::vector<uint16_t> sym;   // kWindow markers, then the symbols of the wide part
+    size_t n_sym = 0;            // end of the symbols in sym (>= kWindow)
     struct MemberEnd {
-        size_t pos;              // index in sym where the member's data ends
+        size_t pos;              // offset in the text where the member's data ends
         uint32_t crc, isize;     // its trailer
         uint64_t next_off;       // byte offset of what follows the trailer
     };
